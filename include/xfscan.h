@@ -1,0 +1,200 @@
+/*
+ * xfscan.h -- C ABI of libxfscan.so: B200 (sm_100a) kernels for XFMamba's SS2D scan path.
+ *
+ * This is the drop-in boundary.  The reference reaches its native scan through a pybind11 module whose
+ * entry points are
+ *     fwd(u, delta, A, B, C, D?, delta_bias?, delta_softplus, nrows[, oflex]) -> [out, x]
+ *     bwd(u, delta, A, B, C, D?, delta_bias?, dout, x?, delta_softplus, nrows) -> [du, ddelta, dA, dB, dC, dD, ddelta_bias]
+ * (reference: models/selective_scan/csrc/selective_scan/selective_scan.cpp:165-172, 251-260, 364-367; call sites
+ * models/csms6s.py:81-85, 97-108), and its cross-scan/merge through Triton launches
+ * (models/csm_triton.py:403-497) and torch index ops (models/fusion_vmamba.py:189-241).
+ * Each function below replaces one of those; the comment above it cites the interface it replaces.
+ *
+ * Conventions
+ *   - plain C, no torch / ATen types; every pointer is a DEVICE pointer owned by the caller
+ *   - the library never allocates, never synchronises, keeps no global state; work is enqueued on `stream`
+ *   - all tensors are dense row-major ("contiguous") with the shapes written at each function
+ *   - index arithmetic is 64-bit (the reference's is uint32: selective_scan.h:27)
+ *   - return value: 0 = success; >0 = cudaError_t of the launch; <0 = argument error (xfs_error_string)
+ *   - re-entrant and CUDA-graph capturable (no allocation / sync / host state)
+ */
+#ifndef XFSCAN_H_
+#define XFSCAN_H_
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define XFS_API __attribute__((visibility("default")))
+#else
+#define XFS_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* xfs_stream_t; /* cudaStream_t */
+
+/* element types of u / delta / B / C / x (A, D, delta_bias, chunk states and dB/dC accumulators are always f32;
+ * same dtype rules as selective_scan.cpp:175-180) */
+enum { XFS_F32 = 0, XFS_BF16 = 1, XFS_F16 = 2 };
+
+/* scan route sets (models/csm_triton.py:25-35): 0 = cross2d (4 routes), 1 = unidirectional, 2 = bidirectional */
+enum { XFS_SCANS_CROSS2D = 0, XFS_SCANS_UNIDI = 1, XFS_SCANS_BIDI = 2 };
+
+enum {
+    XFS_OK = 0,
+    XFS_ERR_NULL = -1,        /* required pointer is NULL */
+    XFS_ERR_SHAPE = -2,       /* non-positive size, dim % ngroups != 0, dstate > 256, ... */
+    XFS_ERR_DTYPE = -3,       /* unknown dtype enum / unsupported combination */
+    XFS_ERR_ALIGN = -4,       /* base pointer not 16-byte aligned */
+    XFS_ERR_UNSUPPORTED = -5, /* valid request this build has no kernel for (e.g. fused path with L too large) */
+    XFS_ERR_ARCH = -6         /* device is not sm_100 */
+};
+
+XFS_API int xfs_version(void);                    /* ABI version, bumps on incompatible change */
+XFS_API const char* xfs_error_string(int code);   /* static string for negative codes; cudaGetErrorString for positive */
+XFS_API int xfs_device_ok(int device);            /* 0 if `device` is compute capability 10.x, XFS_ERR_ARCH otherwise */
+
+/* length of one scan chunk: the forward kernels store the recurrent state at the end of every chunk so that the
+ * backward can restart from it (same role as `x` of shape (B, dim, n_chunks, 2N) in selective_scan.cpp:225-228,
+ * but only h is kept: (B, dim, n_chunks, N) f32). */
+XFS_API int64_t xfs_chunk_len(void);
+XFS_API int64_t xfs_num_chunks(int64_t seqlen);
+
+/* -------------------------------------------------------------------------------------------------------------
+ * CrossScan / CrossMerge, channel-first.  Replaces CrossScanF / CrossScanTritonF and CrossMergeF /
+ * CrossMergeTritonF (models/csm_triton.py:182-273, 403-497).
+ *   cross_scan : x  (B, C, H, W)  [one_by_one: (B, 4, C, H, W)]  ->  xs (B, 4, C, H*W)      pure permutation
+ *   cross_merge: ys (B, 4, C, H*W) -> y (B, C, H*W), y = (ys0 + flip(ys2)) + T(ys1 + flip(ys3))
+ *                [one_by_one: -> (B, 4, C, H*W), un-routing only]            add order of csm_triton.py:61-62
+ * The backward of each is the other (csm_triton.py:208-225, 249-273).
+ * ----------------------------------------------------------------------------------------------------------- */
+XFS_API int xfs_cross_scan(const void* x, void* xs, int64_t B, int64_t C, int64_t H, int64_t W, int dtype, int scans,
+                   int one_by_one, xfs_stream_t stream);
+XFS_API int xfs_cross_merge(const void* ys, void* y, int64_t B, int64_t C, int64_t H, int64_t W, int dtype, int scans,
+                    int one_by_one, xfs_stream_t stream);
+
+/* -------------------------------------------------------------------------------------------------------------
+ * SwappingScan_multiview / SwappingMerge_multiview (models/fusion_vmamba.py:189-241).
+ *   swap_scan : x, x2 (B, C, L) -> out (B, 2, C, L); out[:,0,c] = even(c) ? x2[:,c] : x[:,c]; out[:,1,c] = the other
+ *   swap_merge: ys (B, 2, C, L) -> y, y2 (B, C, L)  (contiguous split)
+ *   swap_stack: y, y2 (B, C, L) -> ys (B, 2, C, L)  (backward of swap_merge as written, :234-241)
+ * ----------------------------------------------------------------------------------------------------------- */
+XFS_API int xfs_swap_scan(const void* x, const void* x2, void* out, int64_t B, int64_t C, int64_t L, int dtype,
+                  xfs_stream_t stream);
+XFS_API int xfs_swap_merge(const void* ys, void* y, void* y2, int64_t B, int64_t C, int64_t L, int dtype, xfs_stream_t stream);
+XFS_API int xfs_swap_stack(const void* y, const void* y2, void* ys, int64_t B, int64_t C, int64_t L, int dtype,
+                   xfs_stream_t stream);
+
+/* -------------------------------------------------------------------------------------------------------------
+ * Selective scan (S6).  Replaces selective_scan_cuda_oflex.fwd / .bwd (ABI quoted at the top; semantics of
+ * models/csms6s.py:25-68).
+ *   u, delta : (batch, dim, seqlen)  dtype                 A : (dim, dstate) f32
+ *   B, C     : (batch, ngroups, dstate, seqlen) dtype      D, delta_bias : (dim) f32 or NULL
+ *   out      : (batch, dim, seqlen)  out_dtype (f32 when oflex, else dtype)
+ *   states   : (batch, dim, xfs_num_chunks(seqlen), dstate) f32, written by fwd, read by bwd; may be NULL in fwd
+ *              (inference) -- bwd then recomputes them itself into `states` which must still be provided
+ * bwd outputs: du, ddelta (batch, dim, seqlen) dtype;  dA (dim, dstate), dD, ddelta_bias (dim) f32, ACCUMULATED
+ *   into (caller zero-fills, as selective_scan.cpp:331-337 does);  dB, dC (batch, ngroups, dstate, seqlen) f32,
+ *   accumulated into (caller zero-fills and casts to dtype afterwards, selective_scan.cpp:332-333, 360).
+ * ----------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    const void* u;
+    const void* delta;
+    const float* A;
+    const void* B;
+    const void* C;
+    const float* D;          /* nullable */
+    const float* delta_bias; /* nullable */
+    void* out;
+    float* states;           /* nullable */
+    int64_t batch, dim, dstate, seqlen, ngroups;
+    int32_t dtype, out_dtype, delta_softplus, reserved;
+} xfs_scan_fwd_args;
+
+typedef struct {
+    const void* u;
+    const void* delta;
+    const float* A;
+    const void* B;
+    const void* C;
+    const float* D;          /* nullable */
+    const float* delta_bias; /* nullable */
+    const void* dout;        /* (batch, dim, seqlen) dout_dtype */
+    const float* states;     /* from fwd */
+    void* du;
+    void* ddelta;
+    float* dA;
+    float* dB;
+    float* dC;
+    float* dD;               /* nullable iff D is */
+    float* ddelta_bias;      /* nullable iff delta_bias is */
+    int64_t batch, dim, dstate, seqlen, ngroups;
+    int32_t dtype, dout_dtype, delta_softplus, reserved;
+} xfs_scan_bwd_args;
+
+XFS_API int xfs_selective_scan_fwd(const xfs_scan_fwd_args* a, xfs_stream_t stream);
+XFS_API int xfs_selective_scan_bwd(const xfs_scan_bwd_args* a, xfs_stream_t stream);
+
+/* -------------------------------------------------------------------------------------------------------------
+ * Fused SS2D core: y = cross_merge(selective_scan(cross_scan(x), delta, A, Bs, Cs, Ds, delta_bias)) in ONE kernel
+ * (forward) and its gradient in ONE kernel (backward).  Replaces the three-operator sequence of
+ * SS2Dv2.forward_corev2 (models/fusion_vmamba.py:1145, 1170-1174; sibling models/vmamba.py:603, 628-632) and of
+ * each of Cross_SS2Dv5's three streams (models/fusion_vmamba.py:485, 508-512).
+ *   x      : (batch, D, H, W) dtype                        delta : (batch, 4*D, H*W) dtype, in scan order of each route
+ *   A      : (4*D, N) f32                                  Bs,Cs : (batch, 4, N, H*W) dtype, in scan order
+ *   Ds, delta_bias : (4*D) f32 or NULL                     y     : (batch, D, H*W) out_dtype, spatial order
+ *   states : (batch, 4*D, xfs_num_chunks(H*W), N) f32 (nullable in fwd)
+ * bwd: dy (batch, D, H*W) dout_dtype -> dx (batch, D, H, W) dtype, ddelta (batch, 4*D, H*W) dtype, and the
+ *   accumulated f32 dA, dBs, dCs, dDs, ddelta_bias as for xfs_selective_scan_bwd.
+ * Returns XFS_ERR_UNSUPPORTED when the per-channel working set does not fit in shared memory
+ * (xfs_ss2d_supported tells in advance); callers then compose the three stand-alone operators.
+ * ----------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    const void* x;
+    const void* delta;
+    const float* A;
+    const void* Bs;
+    const void* Cs;
+    const float* Ds;         /* nullable */
+    const float* delta_bias; /* nullable */
+    void* y;
+    float* states;           /* nullable */
+    int64_t batch, D, N, H, W;
+    int32_t dtype, out_dtype, delta_softplus, scans;
+} xfs_ss2d_fwd_args;
+
+typedef struct {
+    const void* x;
+    const void* delta;
+    const float* A;
+    const void* Bs;
+    const void* Cs;
+    const float* Ds;
+    const float* delta_bias;
+    const void* dy;
+    const float* states;
+    void* dx;
+    void* ddelta;
+    float* dA;
+    float* dBs;
+    float* dCs;
+    float* dDs;
+    float* ddelta_bias;
+    int64_t batch, D, N, H, W;
+    int32_t dtype, dout_dtype, delta_softplus, scans;
+} xfs_ss2d_bwd_args;
+
+XFS_API int xfs_ss2d_supported(int64_t D, int64_t N, int64_t H, int64_t W, int dtype, int backward);
+XFS_API int xfs_ss2d_fwd(const xfs_ss2d_fwd_args* a, xfs_stream_t stream);
+XFS_API int xfs_ss2d_bwd(const xfs_ss2d_bwd_args* a, xfs_stream_t stream);
+
+/* number of kernels this library has launched since load (process-wide, relaxed atomic): lets bench.py report
+ * `gpu_launches` from a count instead of a guess */
+XFS_API int64_t xfs_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XFSCAN_H_ */

@@ -1,0 +1,401 @@
+"""GPU parity tests (run on the B200 box: ``pytest -m gpu``).  Everything goes through the public operators, i.e.
+through the C ABI of libxfscan.so, and is compared with
+  (1) the committed golden fixtures produced by the reference's own Python (tests/golden/), and
+  (2) the CPU oracle (oracle/) on seeded inputs following the reference's test distributions
+      (models/selective_scan/test_selective_scan.py:153-179; shapes with H != W as models/csm_triton.py:524).
+Contract (BASELINE.json): index routes bit exact; scan outputs and gradients within 1e-4 relative in fp32 and
+2e-2 with bf16 inputs, relative = max|a-b| / max|b| per tensor (conftest.rel_err).
+"""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import bf16_bits_to_f32, f16_bits_to_f32, rel_err
+
+pytestmark = pytest.mark.gpu
+
+TOL32 = 1e-4
+TOL16 = 2e-2
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def t(a, dtype=None):
+    x = torch.from_numpy(np.ascontiguousarray(a)).to(dev())
+    return x if dtype is None else x.to(dtype)
+
+
+def bits(a, dtype):
+    """uint16 bit patterns -> torch 16-bit tensor on the GPU"""
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int16)).to(dev()).view(dtype)
+
+
+def n(x):
+    return x.detach().float().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def xf():
+    import xfmamba_b200
+    from xfmamba_b200 import _lib
+    assert _lib.lib().xfs_device_ok(0) == 0, "not an sm_100 device"
+    return xfmamba_b200
+
+
+# ================================================================================================ routes
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+@pytest.mark.parametrize("scans", [0, 1, 2])
+def test_cross_scan_merge_golden(xf, golden, tag, scans):
+    g = golden("csm")
+    x = t(g[f"{tag}_x"]).requires_grad_(True)
+    xs = xf.cross_scan_fn(x, True, True, False, scans)
+    assert np.array_equal(n(xs), g[f"{tag}_s{scans}_xs"])
+    xs.backward(t(g[f"{tag}_gx"]))
+    assert np.array_equal(n(x.grad), g[f"{tag}_s{scans}_dx"])
+    ys = t(g[f"{tag}_ys"]).requires_grad_(True)
+    y = xf.cross_merge_fn(ys, True, True, False, scans)
+    assert np.array_equal(n(y), g[f"{tag}_s{scans}_y"]), "merge add order must match the reference bit for bit"
+    y.backward(t(g[f"{tag}_gy"]))
+    assert np.array_equal(n(ys.grad), g[f"{tag}_s{scans}_dys"])
+    # one_by_one
+    B, _, C, H, W = g[f"{tag}_ys"].shape
+    a = xf.cross_scan_fn(t(g[f"{tag}_ys"]), True, True, True, scans)
+    assert np.array_equal(n(a).reshape(-1), g[f"{tag}_s{scans}_xs1b1"].reshape(-1))
+    m = xf.cross_merge_fn(t(g[f"{tag}_ys"]), True, True, True, scans)
+    assert np.array_equal(n(m).reshape(-1), g[f"{tag}_s{scans}_y1b1"].reshape(-1))
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_cross_scan_merge_bf16_golden(xf, golden, tag):
+    g = golden("csm")
+    xb = t(g[f"{tag}_x"]).to(torch.bfloat16)
+    xs = xf.cross_scan_fn(xb)
+    assert np.array_equal(xs.view(torch.int16).cpu().numpy().view(np.uint16), g[f"{tag}_bf16_xs"])
+    yb = xf.cross_merge_fn(t(g[f"{tag}_ys"]).to(torch.bfloat16))
+    assert np.array_equal(yb.view(torch.int16).cpu().numpy().view(np.uint16), g[f"{tag}_bf16_y"])
+
+
+@pytest.mark.parametrize("shape", [(2, 5, 56, 57), (1, 3, 57, 58), (3, 2, 1, 7), (1, 1, 33, 1), (2, 7, 14, 14), (1, 2, 64, 64)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_cross_scan_merge_oracle(xf, shape, dtype):
+    B, C, H, W = shape
+    rng = np.random.default_rng(hash(shape) % 2**32)
+    x = rng.standard_normal(shape, dtype=np.float32)
+    ys = rng.standard_normal((B, 4, C, H, W), dtype=np.float32)
+    if dtype == torch.float16:
+        x, ys = x.astype(np.float16), ys.astype(np.float16)
+    for scans in (0, 1, 2):
+        xs = xf.cross_scan_fn(t(x), scans=scans)
+        assert np.array_equal(xs.cpu().numpy(), oracle.cross_scan(x, scans))
+        if dtype == torch.float32:
+            y = xf.cross_merge_fn(t(ys), scans=scans)
+            assert np.array_equal(n(y), oracle.cross_merge(ys.reshape(B, 4, C, H * W), H, W, scans))
+
+
+def test_cross_scan_channel_last_layouts(xf):
+    """layout flags of models/csm_triton.py:22-85 (not used by XFMamba, kept for API parity): compare with permutes"""
+    torch.manual_seed(0)
+    x = torch.randn(2, 3, 5, 4, device=dev())
+    ref = xf.cross_scan_fn(x)                                    # (B,4,C,L)
+    assert torch.equal(xf.cross_scan_fn(x.permute(0, 2, 3, 1).contiguous(), False, True), ref)
+    assert torch.equal(xf.cross_scan_fn(x, True, False), ref.permute(0, 3, 1, 2))
+    ys = torch.randn(2, 4, 3, 5, 4, device=dev())
+    refm = xf.cross_merge_fn(ys)                                 # (B,C,L)
+    assert torch.equal(xf.cross_merge_fn(ys.permute(0, 3, 4, 1, 2).contiguous(), True, False), refm)
+    assert torch.equal(xf.cross_merge_fn(ys, False, True), refm.permute(0, 2, 1))
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_swap_golden(xf, golden, tag):
+    g = golden("swap")
+    x, x2 = t(g[f"{tag}_x"]).requires_grad_(True), t(g[f"{tag}_x2"]).requires_grad_(True)
+    xs = xf.SwappingScan_multiview.apply(x, x2)
+    assert np.array_equal(n(xs), g[f"{tag}_xs"])
+    xs.backward(t(g[f"{tag}_gxs"]))
+    assert np.array_equal(n(x.grad), g[f"{tag}_dx"]) and np.array_equal(n(x2.grad), g[f"{tag}_dx2"])
+    ys = t(g[f"{tag}_ys"]).requires_grad_(True)
+    y, y2 = xf.SwappingMerge_multiview.apply(ys)
+    assert np.array_equal(n(y), g[f"{tag}_y"]) and np.array_equal(n(y2), g[f"{tag}_y2"])
+    (y * t(g[f"{tag}_gy"])).sum().add((y2 * t(g[f"{tag}_gy2"])).sum()).backward()
+    assert np.array_equal(n(ys.grad), g[f"{tag}_dys"])
+    # the exact adjoint (opt-in) differs from the reference's as-written backward on even channels only
+    xa, xb = t(g[f"{tag}_x"]).requires_grad_(True), t(g[f"{tag}_x2"]).requires_grad_(True)
+    xf.swapping_scan(xa, xb, exact_adjoint=True).backward(t(g[f"{tag}_gxs"]))
+    gx = g[f"{tag}_gxs"]
+    B, C, H, W = g[f"{tag}_x"].shape
+    exp = np.where((np.arange(C) % 2 == 0)[None, :, None], gx[:, 1], gx[:, 0]).reshape(B, C, H, W)
+    assert np.array_equal(n(xa.grad), exp)
+
+
+# ================================================================================================ selective scan
+def _golden_case(g, name):
+    meta = [int(v) for v in g[f"{name}_meta"]]
+    Bsz, K, Cd, N, L, has_D, has_bias, softplus, oflex, dt = meta
+    tdt = {0: torch.float32, 1: torch.bfloat16, 2: torch.float16}[dt]
+    mk = (lambda a: t(a)) if dt == 0 else (lambda a: bits(a, tdt))
+    ten = {k: mk(g[f"{name}_{k}"]) for k in ("u", "delta", "B", "C")}
+    ten["A"] = t(g[f"{name}_A"])
+    ten["D"] = t(g[f"{name}_D"]) if has_D else None
+    ten["delta_bias"] = t(g[f"{name}_delta_bias"]) if has_bias else None
+    return ten, bool(softplus), bool(oflex), dt
+
+
+GRAD_KEYS = ["u", "delta", "A", "B", "C", "D", "delta_bias"]
+
+
+@pytest.mark.parametrize("name", ["s1", "s2", "s3", "s4", "s5", "s6", "h1", "h2", "h3"])
+def test_selective_scan_golden(xf, golden, name):
+    g = golden("scan")
+    ten, softplus, oflex, dt = _golden_case(g, name)
+    leaves = {k: (v.clone().requires_grad_(True) if v is not None else None) for k, v in ten.items()}
+    out = xf.selective_scan_fn(leaves["u"], leaves["delta"], leaves["A"], leaves["B"], leaves["C"], leaves["D"],
+                               leaves["delta_bias"], softplus, oflex)
+    conv = {0: lambda a: a, 1: bf16_bits_to_f32, 2: f16_bits_to_f32}[dt]
+    ref_out = g[f"{name}_out"] if (oflex or dt == 0) else conv(g[f"{name}_out"])
+    assert out.dtype == (torch.float32 if oflex else ten["u"].dtype)          # models/csms6s.py:68
+    tol = TOL32 if dt == 0 else TOL16
+    assert rel_err(n(out), ref_out) < tol
+    out.backward(t(g[f"{name}_dout"]).to(out.dtype))
+    for k in GRAD_KEYS:
+        if leaves[k] is None:
+            continue
+        ref = g[f"{name}_d{k}"]
+        ref = ref if ref.dtype == np.float32 else conv(ref)
+        assert leaves[k].grad.dtype == leaves[k].dtype
+        assert rel_err(n(leaves[k].grad), ref) < tol, f"{name}: d{k}"
+
+
+def _rand_scan(rng, Bsz, K, Cd, N, L):
+    """input distributions of models/selective_scan/test_selective_scan.py:157-179"""
+    KD = K * Cd
+    f = lambda *s: rng.standard_normal(s, dtype=np.float32)
+    r = lambda *s: rng.random(s, dtype=np.float32)
+    return dict(u=f(Bsz, KD, L), delta=0.5 * r(Bsz, KD, L), A=-0.5 * r(KD, N), B=f(Bsz, K, N, L), C=f(Bsz, K, N, L),
+                D=f(KD), delta_bias=0.5 * r(KD), dout=f(Bsz, KD, L))
+
+
+@pytest.mark.parametrize("seqlen", [64, 128, 256, 372, 512, 784, 1024, 1134, 2048, 4096])
+@pytest.mark.parametrize("groups", [1, 2])
+def test_selective_scan_reference_grid_fp32(xf, seqlen, groups):
+    """the reference's own pytest grid (test_selective_scan.py:137-156): batch 2, dim 24, dstate 8, seed 0"""
+    rng = np.random.default_rng(seqlen * 10 + groups)
+    c = _rand_scan(rng, 2, groups, 24 // groups, 8, seqlen)
+    has_D, has_bias, softplus = True, True, True
+    leaves = {k: t(c[k]).requires_grad_(True) for k in GRAD_KEYS}
+    out = xf.selective_scan_fn(leaves["u"], leaves["delta"], leaves["A"], leaves["B"], leaves["C"], leaves["D"],
+                               leaves["delta_bias"], softplus, True)
+    ref = oracle.selective_scan_fwd(c["u"], c["delta"], c["A"], c["B"], c["C"], c["D"], c["delta_bias"], softplus, "f64")
+    assert rel_err(n(out), ref) < TOL32
+    out.backward(t(c["dout"]))
+    grads = oracle.selective_scan_bwd(c["u"], c["delta"], c["A"], c["B"], c["C"], c["D"], c["delta_bias"], c["dout"], softplus, "f64")
+    for k, gr in zip(GRAD_KEYS, grads):
+        assert rel_err(n(leaves[k].grad), gr) < TOL32, f"d{k}"
+
+
+@pytest.mark.parametrize("flags", [(False, False, False), (True, False, True), (False, True, False), (False, True, True)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_selective_scan_flags_and_dtypes(xf, flags, dtype):
+    has_D, has_bias, softplus = flags
+    rng = np.random.default_rng(7)
+    c = _rand_scan(rng, 2, 2, 5, 3, 300)
+    if dtype != torch.float32:   # quantise the 16-bit tensors first so that oracle and kernel see identical inputs
+        for k in ("u", "delta", "B", "C"):
+            c[k] = t(c[k]).to(dtype).float().cpu().numpy()
+    D = c["D"] if has_D else None
+    bias = c["delta_bias"] if has_bias else None
+    leaves = {k: t(c[k]).to(dtype if k in ("u", "delta", "B", "C") else torch.float32).requires_grad_(True) for k in GRAD_KEYS}
+    out = xf.selective_scan_fn(leaves["u"], leaves["delta"], leaves["A"], leaves["B"], leaves["C"],
+                               leaves["D"] if has_D else None, leaves["delta_bias"] if has_bias else None, softplus, True)
+    assert out.dtype == torch.float32
+    ref = oracle.selective_scan_fwd(c["u"], c["delta"], c["A"], c["B"], c["C"], D, bias, softplus, "f64")
+    assert rel_err(n(out), ref) < TOL32          # fp32 arithmetic inside: 16-bit inputs only quantise the inputs
+    out.backward(t(c["dout"]))
+    grads = oracle.selective_scan_bwd(c["u"], c["delta"], c["A"], c["B"], c["C"], D, bias, c["dout"], softplus, "f64")
+    tol = TOL32 if dtype == torch.float32 else TOL16       # 16-bit grads are rounded to the input dtype on store
+    for k, gr in zip(GRAD_KEYS, grads):
+        if gr is None:
+            assert leaves[k].grad is None
+            continue
+        assert rel_err(n(leaves[k].grad), gr) < tol, f"d{k}"
+
+
+def test_selective_scan_softplus_threshold_and_extremes(xf):
+    """x > 20 passes through; very negative x underflows to 0 without NaN (models/csms6s.py:49-50)"""
+    rng = np.random.default_rng(3)
+    c = _rand_scan(rng, 1, 1, 4, 2, 96)
+    c["delta"] = (rng.random((1, 4, 96), dtype=np.float32) * 140.0 - 70.0)
+    out = xf.selective_scan_fn(t(c["u"]), t(c["delta"]), t(c["A"]), t(c["B"]), t(c["C"]), t(c["D"]), t(c["delta_bias"]), True, True)
+    ref = oracle.selective_scan_fwd(c["u"], c["delta"], c["A"], c["B"], c["C"], c["D"], c["delta_bias"], True, "f64")
+    assert torch.isfinite(out).all()
+    assert rel_err(n(out), ref) < TOL32
+
+
+def test_selective_scan_argument_errors(xf):
+    d = dev()
+    u = torch.randn(2, 6, 16, device=d)
+    A = torch.randn(6, 4, device=d)
+    Bm = torch.randn(2, 2, 4, 16, device=d)
+    with pytest.raises(RuntimeError, match="float32"):
+        xf.selective_scan_fn(u, u, A.half(), Bm, Bm)
+    with pytest.raises(RuntimeError, match="share one dtype"):
+        xf.selective_scan_fn(u, u.half(), A, Bm, Bm)
+    with pytest.raises(RuntimeError, match="dividable"):
+        xf.selective_scan_fn(u, u, A, torch.randn(2, 4, 4, 16, device=d), torch.randn(2, 4, 4, 16, device=d))
+    with pytest.raises(RuntimeError, match="delta"):
+        xf.selective_scan_fn(u, u[:, :, :8], A, Bm, Bm)
+    # empty batch is a no-op, as in torch
+    e = xf.selective_scan_fn(u[:0], u[:0], A, Bm[:0], Bm[:0])
+    assert e.shape == (0, 6, 16)
+
+
+# ================================================================================================ fused SS2D core
+def _rand_ss2d(rng, Bsz, D, N, H, W, model_like=False):
+    L = H * W
+    f = lambda *s: rng.standard_normal(s, dtype=np.float32)
+    r = lambda *s: rng.random(s, dtype=np.float32)
+    c = dict(x=f(Bsz, D, H, W), delta=0.5 * r(Bsz, 4 * D, L), A=-0.5 * r(4 * D, N), Bs=f(Bsz, 4, N, L), Cs=f(Bsz, 4, N, L),
+             Ds=f(4 * D), delta_bias=0.5 * r(4 * D), dy=f(Bsz, D, L))
+    if model_like:    # A = -(1..N), dt in [1e-3, 1e-1] (models/fusion_vmamba.py:303-328)
+        c["A"] = -np.tile(np.arange(1, N + 1, dtype=np.float32), (4 * D, 1))
+        dt = np.exp(r(4 * D) * (np.log(0.1) - np.log(0.001)) + np.log(0.001)).astype(np.float32)
+        c["delta_bias"] = (dt + np.log(-np.expm1(-dt))).astype(np.float32)
+        c["delta"] = 0.3 * f(Bsz, 4 * D, L)
+    return c
+
+
+SS2D_KEYS = ["x", "delta", "A", "Bs", "Cs", "Ds", "delta_bias"]
+
+
+def _run_ss2d(xf, c, dtype=torch.float32, oflex=True, has_D=True, has_bias=True):
+    leaves = {k: t(c[k]).to(dtype if k in ("x", "delta", "Bs", "Cs") else torch.float32).requires_grad_(True) for k in SS2D_KEYS}
+    y = xf.ss2d_scan(leaves["x"], leaves["delta"], leaves["A"], leaves["Bs"], leaves["Cs"],
+                     leaves["Ds"] if has_D else None, leaves["delta_bias"] if has_bias else None, True, oflex)
+    y.backward(t(c["dy"]).to(y.dtype))
+    return y, leaves
+
+
+def test_ss2d_golden_core(xf, golden):
+    """operator-level tensors recorded inside the reference's SS2Dv2.forward_corev2 (models/fusion_vmamba.py:1176-1181)"""
+    g = golden("cores")
+    x = t(g["ss2d_x"])
+    y = xf.ss2d_scan(x, t(g["ss2d_dts"]), t(g["ss2d_As"]), t(g["ss2d_Bs"]), t(g["ss2d_Cs"]), t(g["ss2d_Ds"]), t(g["ss2d_delta_bias"]))
+    assert rel_err(n(y), g["ss2d_ymerged"]) < TOL32
+    # and the unfused drop-in chain gives the same tensors the reference recorded
+    B, D, H, W = x.shape
+    xs = xf.cross_scan_fn(x)
+    assert np.array_equal(n(xs).reshape(B, 4 * D, H * W), g["ss2d_us"])
+    ys = xf.selective_scan_fn(xs.view(B, -1, H * W), t(g["ss2d_dts"]), t(g["ss2d_As"]), t(g["ss2d_Bs"]), t(g["ss2d_Cs"]),
+                              t(g["ss2d_Ds"]), t(g["ss2d_delta_bias"]), True, True)
+    assert rel_err(n(ys), g["ss2d_ys"].reshape(B, 4 * D, H * W)) < TOL32
+    assert rel_err(n(xf.cross_merge_fn(ys.view(B, 4, D, H, W))), g["ss2d_ymerged"]) < TOL32
+
+
+@pytest.mark.parametrize("shape", [
+    (2, 4, 1, 6, 5), (1, 3, 1, 14, 14), (2, 6, 1, 28, 28), (1, 5, 1, 17, 19), (1, 2, 1, 56, 57), (2, 2, 1, 7, 7),
+    (1, 2, 4, 7, 7), (2, 3, 16, 7, 7), (1, 2, 3, 16, 17), (1, 1, 1, 1, 300), (1, 2, 1, 32, 8),
+])
+@pytest.mark.parametrize("model_like", [False, True])
+def test_ss2d_fused_oracle_fp32(xf, shape, model_like):
+    Bsz, D, N, H, W = shape
+    rng = np.random.default_rng(abs(hash(shape)) % 2**32)
+    c = _rand_ss2d(rng, Bsz, D, N, H, W, model_like)
+    assert xf.ss2d_fused_supported(D, N, H, W, torch.float32, True)
+    y, leaves = _run_ss2d(xf, c)
+    ref = oracle.ss2d_fwd(c["x"], c["delta"], c["A"], c["Bs"], c["Cs"], c["Ds"], c["delta_bias"], True, "f64")
+    assert rel_err(n(y), ref) < TOL32
+    grads = oracle.ss2d_bwd(c["x"], c["delta"], c["A"], c["Bs"], c["Cs"], c["Ds"], c["delta_bias"], c["dy"], True, "f64")
+    for k, gr in zip(SS2D_KEYS, grads):
+        assert rel_err(n(leaves[k].grad), gr) < TOL32, f"d{k}"
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("oflex", [True, False])
+def test_ss2d_fused_16bit(xf, dtype, oflex):
+    rng = np.random.default_rng(11)
+    c = _rand_ss2d(rng, 2, 4, 1, 16, 24)
+    for k in ("x", "delta", "Bs", "Cs"):
+        c[k] = t(c[k]).to(dtype).float().cpu().numpy()
+    y, leaves = _run_ss2d(xf, c, dtype, oflex)
+    assert y.dtype == (torch.float32 if oflex else dtype)
+    ref = oracle.ss2d_fwd(c["x"], c["delta"], c["A"], c["Bs"], c["Cs"], c["Ds"], c["delta_bias"], True, "f64")
+    assert rel_err(n(y), ref) < (TOL32 if oflex else TOL16)
+    grads = oracle.ss2d_bwd(c["x"], c["delta"], c["A"], c["Bs"], c["Cs"], c["Ds"], c["delta_bias"], c["dy"], True, "f64")
+    for k, gr in zip(SS2D_KEYS, grads):
+        assert rel_err(n(leaves[k].grad), gr) < TOL16, f"d{k}"
+
+
+def test_ss2d_fused_optional_params(xf):
+    rng = np.random.default_rng(5)
+    c = _rand_ss2d(rng, 1, 3, 1, 9, 11)
+    y, leaves = _run_ss2d(xf, c, has_D=False, has_bias=False)
+    ref = oracle.ss2d_fwd(c["x"], c["delta"], c["A"], c["Bs"], c["Cs"], None, None, True, "f64")
+    assert rel_err(n(y), ref) < TOL32
+    assert leaves["Ds"].grad is None and leaves["delta_bias"].grad is None
+
+
+def test_ss2d_full_size_properties(xf):
+    """config-2 shape (56x56, D=192, N=1, K=4) at a size the CPU oracle cannot reach: size-independent properties.
+    (1) fused == composition of the three stand-alone CUDA operators, forward and all gradients;
+    (2) route symmetry: rotating the image by 180 degrees and exchanging the parameters of routes (0,2) and (1,3)
+        rotates the output (route 2/3 are the flips of routes 0/1, models/csm_triton.py:29)."""
+    torch.manual_seed(0)
+    d = dev()
+    Bsz, D, H, W, N = 8, 192, 56, 56, 1
+    L = H * W
+    x = torch.randn(Bsz, D, H, W, device=d)
+    delta = 0.5 * torch.rand(Bsz, 4 * D, L, device=d)
+    A = -0.5 * torch.rand(4 * D, N, device=d)
+    Bs, Cs = torch.randn(Bsz, 4, N, L, device=d), torch.randn(Bsz, 4, N, L, device=d)
+    Ds, bias = torch.randn(4 * D, device=d), 0.5 * torch.rand(4 * D, device=d)
+    dy = torch.randn(Bsz, D, L, device=d)
+
+    def run(fused):
+        lv = [v.clone().requires_grad_(True) for v in (x, delta, A, Bs, Cs, Ds, bias)]
+        if fused:
+            y = xf.ss2d_scan(*lv)
+        else:
+            xs = xf.cross_scan_fn(lv[0]).view(Bsz, -1, L)
+            ys = xf.selective_scan_fn(xs, *lv[1:], True, True)
+            y = xf.cross_merge_fn(ys.view(Bsz, 4, D, H, W))
+        y.backward(dy)
+        return y, [v.grad for v in lv]
+
+    yf, gf = run(True)
+    yu, gu = run(False)
+    assert rel_err(n(yf), n(yu)) < TOL32
+    for k, a, b in zip(SS2D_KEYS, gf, gu):
+        assert rel_err(n(a), n(b)) < TOL32, f"d{k}"
+
+    def swap_routes(v, lead):          # exchange route blocks (0<->2, 1<->3) along the dim that holds 4 routes
+        shp = v.shape
+        v4 = v.reshape(*shp[:lead], 4, -1)
+        return v4[(slice(None),) * lead + ([2, 3, 0, 1],)].reshape(shp)
+
+    y_rot = xf.ss2d_scan(x.flip(2, 3), swap_routes(delta, 1), swap_routes(A, 0), swap_routes(Bs, 1), swap_routes(Cs, 1),
+                         swap_routes(Ds, 0), swap_routes(bias, 0))
+    assert rel_err(n(y_rot), n(yf.flip(2))) < TOL32
+
+
+def test_ss2d_unfused_fallback_large_L(xf):
+    """L too large for the fused working set -> the operator composes the stand-alone kernels (still CUDA)"""
+    rng = np.random.default_rng(9)
+    H, W = 128, 128
+    assert not xf.ss2d_fused_supported(2, 1, H, W, torch.float32, True)
+    c = _rand_ss2d(rng, 1, 2, 1, H, W)
+    y, leaves = _run_ss2d(xf, c)
+    ref = oracle.ss2d_fwd(c["x"], c["delta"], c["A"], c["Bs"], c["Cs"], c["Ds"], c["delta_bias"], True, "f64")
+    assert rel_err(n(y), ref) < TOL32
+    grads = oracle.ss2d_bwd(c["x"], c["delta"], c["A"], c["Bs"], c["Cs"], c["Ds"], c["delta_bias"], c["dy"], True, "f64")
+    for k, gr in zip(SS2D_KEYS, grads):
+        assert rel_err(n(leaves[k].grad), gr) < TOL32, f"d{k}"
+
+
+def test_native_library_was_used(xf):
+    """the driver checks which .so the test process loaded; make the launch counter prove it too"""
+    from xfmamba_b200 import _lib
+    before = _lib.launch_count()
+    xf.cross_scan_fn(torch.randn(1, 1, 4, 4, device=dev()))
+    assert _lib.launch_count() == before + 1

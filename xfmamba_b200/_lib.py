@@ -1,0 +1,136 @@
+"""ctypes binding of ``libxfscan.so`` (C ABI in ``include/xfscan.h``).
+
+PyTorch is only the allocator / stream provider here: every call passes raw device pointers and the current CUDA
+stream.  There is NO CPU path and NO fallback: if the shared library is missing or the tensors are not on a CUDA
+device the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from pathlib import Path
+
+import torch
+
+_PKG = Path(__file__).resolve().parent
+_SO = _PKG / "libxfscan.so"
+_lib = None
+
+F32, BF16, F16 = 0, 1, 2
+_DTYPES = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}
+
+c_i64, c_i32, c_vp = ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p
+
+
+class ScanFwdArgs(ctypes.Structure):
+    _fields_ = [(n, c_vp) for n in ("u", "delta", "A", "B", "C", "D", "delta_bias", "out", "states")] + \
+               [(n, c_i64) for n in ("batch", "dim", "dstate", "seqlen", "ngroups")] + \
+               [(n, c_i32) for n in ("dtype", "out_dtype", "delta_softplus", "reserved")]
+
+
+class ScanBwdArgs(ctypes.Structure):
+    _fields_ = [(n, c_vp) for n in ("u", "delta", "A", "B", "C", "D", "delta_bias", "dout", "states", "du", "ddelta",
+                                    "dA", "dB", "dC", "dD", "ddelta_bias")] + \
+               [(n, c_i64) for n in ("batch", "dim", "dstate", "seqlen", "ngroups")] + \
+               [(n, c_i32) for n in ("dtype", "dout_dtype", "delta_softplus", "reserved")]
+
+
+class Ss2dFwdArgs(ctypes.Structure):
+    _fields_ = [(n, c_vp) for n in ("x", "delta", "A", "Bs", "Cs", "Ds", "delta_bias", "y", "states")] + \
+               [(n, c_i64) for n in ("batch", "D", "N", "H", "W")] + \
+               [(n, c_i32) for n in ("dtype", "out_dtype", "delta_softplus", "scans")]
+
+
+class Ss2dBwdArgs(ctypes.Structure):
+    _fields_ = [(n, c_vp) for n in ("x", "delta", "A", "Bs", "Cs", "Ds", "delta_bias", "dy", "states", "dx", "ddelta",
+                                    "dA", "dBs", "dCs", "dDs", "ddelta_bias")] + \
+               [(n, c_i64) for n in ("batch", "D", "N", "H", "W")] + \
+               [(n, c_i32) for n in ("dtype", "dout_dtype", "delta_softplus", "scans")]
+
+
+# every symbol include/xfscan.h declares (tests/test_cabi.py checks the .so exports all of them)
+SYMBOLS = [
+    "xfs_version", "xfs_error_string", "xfs_device_ok", "xfs_chunk_len", "xfs_num_chunks", "xfs_launch_count",
+    "xfs_cross_scan", "xfs_cross_merge", "xfs_swap_scan", "xfs_swap_merge", "xfs_swap_stack",
+    "xfs_selective_scan_fwd", "xfs_selective_scan_bwd", "xfs_ss2d_supported", "xfs_ss2d_fwd", "xfs_ss2d_bwd",
+]
+
+
+def library_path() -> Path:
+    return _SO
+
+
+def lib() -> ctypes.CDLL:
+    """Loads the library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _SO.exists():
+        raise ImportError(
+            f"{_SO} is missing: build it with `python -m xfmamba_b200.build` (needs nvcc, targets sm_100a). "
+            "xfmamba_b200 has no CPU or PyTorch fallback.")
+    L = ctypes.CDLL(str(_SO))
+    L.xfs_version.restype = ctypes.c_int
+    L.xfs_error_string.restype = ctypes.c_char_p
+    L.xfs_error_string.argtypes = [ctypes.c_int]
+    L.xfs_device_ok.argtypes = [ctypes.c_int]
+    L.xfs_chunk_len.restype = c_i64
+    L.xfs_num_chunks.restype = c_i64
+    L.xfs_num_chunks.argtypes = [c_i64]
+    L.xfs_launch_count.restype = c_i64
+    for name in ("xfs_cross_scan", "xfs_cross_merge"):
+        getattr(L, name).argtypes = [c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp]
+    L.xfs_swap_scan.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, ctypes.c_int, c_vp]
+    L.xfs_swap_merge.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, ctypes.c_int, c_vp]
+    L.xfs_swap_stack.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, ctypes.c_int, c_vp]
+    L.xfs_selective_scan_fwd.argtypes = [ctypes.POINTER(ScanFwdArgs), c_vp]
+    L.xfs_selective_scan_bwd.argtypes = [ctypes.POINTER(ScanBwdArgs), c_vp]
+    L.xfs_ss2d_supported.argtypes = [c_i64, c_i64, c_i64, c_i64, ctypes.c_int, ctypes.c_int]
+    L.xfs_ss2d_fwd.argtypes = [ctypes.POINTER(Ss2dFwdArgs), c_vp]
+    L.xfs_ss2d_bwd.argtypes = [ctypes.POINTER(Ss2dBwdArgs), c_vp]
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().xfs_error_string(rc).decode()
+        raise RuntimeError(f"{what}: {msg} (code {rc})")
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise RuntimeError(f"xfmamba_b200: unsupported dtype {t.dtype}; expected float32, bfloat16 or float16") from None
+
+
+def require_cuda(*tensors: torch.Tensor) -> torch.device:
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("xfmamba_b200 operators run on CUDA tensors only (sm_100a kernels, no CPU fallback); "
+                               f"got a tensor on {t.device}")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"xfmamba_b200: tensors on different devices ({dev} vs {t.device})")
+    return dev
+
+
+def ptr(t):
+    return None if t is None else c_vp(t.data_ptr())
+
+
+def stream(dev: torch.device):
+    return c_vp(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def num_chunks(L: int) -> int:
+    return int(lib().xfs_num_chunks(int(L)))
+
+
+def launch_count() -> int:
+    return int(lib().xfs_launch_count())

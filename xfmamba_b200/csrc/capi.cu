@@ -1,0 +1,145 @@
+// capi.cu -- the extern "C" surface declared in include/xfscan.h: argument checks (mirroring the TORCH_CHECKs of the
+// reference's selective_scan.cpp:173-223, reported as negative codes instead of exceptions) and dispatch.
+#include <atomic>
+
+#include "xfscan_common.cuh"
+
+namespace xfs {
+
+int launch_cross_scan(const void*, void*, int64_t, int64_t, int64_t, int64_t, int, int, int, cudaStream_t);
+int launch_cross_merge(const void*, void*, int64_t, int64_t, int64_t, int64_t, int, int, int, cudaStream_t);
+int launch_swap(const void*, const void*, void*, void*, int64_t, int64_t, int64_t, int, int, cudaStream_t);
+int launch_scan_fwd(const xfs_scan_fwd_args&, cudaStream_t);
+int launch_scan_bwd(const xfs_scan_bwd_args&, cudaStream_t);
+int launch_ss2d_fwd(const xfs_ss2d_fwd_args&, cudaStream_t);
+int launch_ss2d_bwd(const xfs_ss2d_bwd_args&, cudaStream_t);
+int ss2d_supported(int64_t, int64_t, int64_t, int64_t, int, int);
+
+static std::atomic<long long> g_launches{0};
+
+int check_launch() {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return (int)cudaGetLastError();
+}
+
+static inline bool bad_dtype(int dt) { return dt != XFS_F32 && dt != XFS_BF16 && dt != XFS_F16; }
+static inline bool bad_scans(int s) { return s != XFS_SCANS_CROSS2D && s != XFS_SCANS_UNIDI && s != XFS_SCANS_BIDI; }
+static inline bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) != 0; }
+
+}  // namespace xfs
+
+using namespace xfs;
+
+extern "C" {
+
+int xfs_version(void) { return 1; }
+
+const char* xfs_error_string(int code) {
+    switch (code) {
+        case XFS_OK: return "ok";
+        case XFS_ERR_NULL: return "xfscan: a required pointer is NULL";
+        case XFS_ERR_SHAPE: return "xfscan: invalid shape (sizes must be positive, dim % ngroups == 0, dstate <= 256)";
+        case XFS_ERR_DTYPE: return "xfscan: unsupported dtype (u/delta/B/C must share one of f32/bf16/f16; out is f32 or that dtype)";
+        case XFS_ERR_ALIGN: return "xfscan: tensor base pointers must be 16-byte aligned";
+        case XFS_ERR_UNSUPPORTED: return "xfscan: no kernel for this request (fused SS2D working set exceeds shared memory, or scans != 0)";
+        case XFS_ERR_ARCH: return "xfscan: device is not compute capability 10.x (built for sm_100a only)";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "xfscan: unknown error";
+    }
+}
+
+int xfs_device_ok(int device) {
+    cudaDeviceProp prop;
+    const cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return (int)e;
+    return prop.major == 10 ? XFS_OK : XFS_ERR_ARCH;
+}
+
+int64_t xfs_chunk_len(void) { return kChunk; }
+int64_t xfs_num_chunks(int64_t seqlen) { return (seqlen + kChunk - 1) / kChunk; }
+int64_t xfs_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int xfs_cross_scan(const void* x, void* xs, int64_t B, int64_t C, int64_t H, int64_t W, int dtype, int scans,
+                   int one_by_one, xfs_stream_t stream) {
+    if (!x || !xs) return XFS_ERR_NULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || H > 65535 * 32 || W > 65535 * 32) return XFS_ERR_SHAPE;
+    if (bad_dtype(dtype)) return XFS_ERR_DTYPE;
+    if (bad_scans(scans)) return XFS_ERR_UNSUPPORTED;
+    return launch_cross_scan(x, xs, B, C, H, W, dtype, scans, one_by_one != 0, (cudaStream_t)stream);
+}
+
+int xfs_cross_merge(const void* ys, void* y, int64_t B, int64_t C, int64_t H, int64_t W, int dtype, int scans,
+                    int one_by_one, xfs_stream_t stream) {
+    if (!ys || !y) return XFS_ERR_NULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || H > 65535 * 32 || W > 65535 * 32) return XFS_ERR_SHAPE;
+    if (bad_dtype(dtype)) return XFS_ERR_DTYPE;
+    if (bad_scans(scans)) return XFS_ERR_UNSUPPORTED;
+    return launch_cross_merge(ys, y, B, C, H, W, dtype, scans, one_by_one != 0, (cudaStream_t)stream);
+}
+
+int xfs_swap_scan(const void* x, const void* x2, void* out, int64_t B, int64_t C, int64_t L, int dtype, xfs_stream_t stream) {
+    if (!x || !x2 || !out) return XFS_ERR_NULL;
+    if (B <= 0 || C <= 0 || L <= 0) return XFS_ERR_SHAPE;
+    if (bad_dtype(dtype)) return XFS_ERR_DTYPE;
+    return launch_swap(x, x2, out, nullptr, B, C, L, dtype, 0, (cudaStream_t)stream);
+}
+
+int xfs_swap_merge(const void* ys, void* y, void* y2, int64_t B, int64_t C, int64_t L, int dtype, xfs_stream_t stream) {
+    if (!ys || !y || !y2) return XFS_ERR_NULL;
+    if (B <= 0 || C <= 0 || L <= 0) return XFS_ERR_SHAPE;
+    if (bad_dtype(dtype)) return XFS_ERR_DTYPE;
+    return launch_swap(ys, nullptr, y, y2, B, C, L, dtype, 1, (cudaStream_t)stream);
+}
+
+int xfs_swap_stack(const void* y, const void* y2, void* ys, int64_t B, int64_t C, int64_t L, int dtype, xfs_stream_t stream) {
+    if (!y || !y2 || !ys) return XFS_ERR_NULL;
+    if (B <= 0 || C <= 0 || L <= 0) return XFS_ERR_SHAPE;
+    if (bad_dtype(dtype)) return XFS_ERR_DTYPE;
+    return launch_swap(y, y2, ys, nullptr, B, C, L, dtype, 2, (cudaStream_t)stream);
+}
+
+int xfs_selective_scan_fwd(const xfs_scan_fwd_args* a, xfs_stream_t stream) {
+    if (!a || !a->u || !a->delta || !a->A || !a->B || !a->C || !a->out) return XFS_ERR_NULL;
+    if (a->batch <= 0 || a->dim <= 0 || a->dstate <= 0 || a->seqlen <= 0 || a->ngroups <= 0) return XFS_ERR_SHAPE;
+    if (a->dim % a->ngroups != 0 || a->dstate > 256) return XFS_ERR_SHAPE;       // selective_scan.cpp:198-199
+    if (bad_dtype(a->dtype) || (a->out_dtype != XFS_F32 && a->out_dtype != a->dtype)) return XFS_ERR_DTYPE;
+    return launch_scan_fwd(*a, (cudaStream_t)stream);
+}
+
+int xfs_selective_scan_bwd(const xfs_scan_bwd_args* a, xfs_stream_t stream) {
+    if (!a || !a->u || !a->delta || !a->A || !a->B || !a->C || !a->dout || !a->states || !a->du || !a->ddelta || !a->dA ||
+        !a->dB || !a->dC)
+        return XFS_ERR_NULL;
+    if ((a->D != nullptr) != (a->dD != nullptr) || (a->delta_bias != nullptr) != (a->ddelta_bias != nullptr)) return XFS_ERR_NULL;
+    if (a->batch <= 0 || a->dim <= 0 || a->dstate <= 0 || a->seqlen <= 0 || a->ngroups <= 0) return XFS_ERR_SHAPE;
+    if (a->dim % a->ngroups != 0 || a->dstate > 256) return XFS_ERR_SHAPE;
+    if (bad_dtype(a->dtype) || (a->dout_dtype != XFS_F32 && a->dout_dtype != a->dtype)) return XFS_ERR_DTYPE;
+    return launch_scan_bwd(*a, (cudaStream_t)stream);
+}
+
+int xfs_ss2d_supported(int64_t D, int64_t N, int64_t H, int64_t W, int dtype, int backward) {
+    if (D <= 0 || N <= 0 || H <= 0 || W <= 0 || bad_dtype(dtype)) return 0;
+    return ss2d_supported(D, N, H, W, dtype, backward);
+}
+
+int xfs_ss2d_fwd(const xfs_ss2d_fwd_args* a, xfs_stream_t stream) {
+    if (!a || !a->x || !a->delta || !a->A || !a->Bs || !a->Cs || !a->y) return XFS_ERR_NULL;
+    if (a->batch <= 0 || a->D <= 0 || a->N <= 0 || a->H <= 0 || a->W <= 0) return XFS_ERR_SHAPE;
+    if (bad_dtype(a->dtype) || (a->out_dtype != XFS_F32 && a->out_dtype != a->dtype)) return XFS_ERR_DTYPE;
+    if (a->scans != XFS_SCANS_CROSS2D) return XFS_ERR_UNSUPPORTED;
+    if (!ss2d_supported(a->D, a->N, a->H, a->W, a->dtype, 0)) return XFS_ERR_UNSUPPORTED;
+    return launch_ss2d_fwd(*a, (cudaStream_t)stream);
+}
+
+int xfs_ss2d_bwd(const xfs_ss2d_bwd_args* a, xfs_stream_t stream) {
+    if (!a || !a->x || !a->delta || !a->A || !a->Bs || !a->Cs || !a->dy || !a->states || !a->dx || !a->ddelta || !a->dA ||
+        !a->dBs || !a->dCs)
+        return XFS_ERR_NULL;
+    if ((a->Ds != nullptr) != (a->dDs != nullptr) || (a->delta_bias != nullptr) != (a->ddelta_bias != nullptr)) return XFS_ERR_NULL;
+    if (a->batch <= 0 || a->D <= 0 || a->N <= 0 || a->H <= 0 || a->W <= 0) return XFS_ERR_SHAPE;
+    if (bad_dtype(a->dtype) || (a->dout_dtype != XFS_F32 && a->dout_dtype != a->dtype)) return XFS_ERR_DTYPE;
+    if (a->scans != XFS_SCANS_CROSS2D) return XFS_ERR_UNSUPPORTED;
+    if (!ss2d_supported(a->D, a->N, a->H, a->W, a->dtype, 1)) return XFS_ERR_UNSUPPORTED;
+    return launch_ss2d_bwd(*a, (cudaStream_t)stream);
+}
+
+}  // extern "C"

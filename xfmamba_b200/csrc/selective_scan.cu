@@ -1,0 +1,263 @@
+// selective_scan.cu -- stand-alone S6 selective scan, forward and backward, any dstate / ngroups / seqlen.
+//
+// Replaces selective_scan_fwd_kernel / selective_scan_bwd_kernel of the reference's native extension
+// (models/selective_scan/csrc/selective_scan/selective_scan_fwd_kernel.cuh:62-206, selective_scan_bwd_kernel.cuh:66-274)
+// with the semantics of selective_scan_torch (models/csms6s.py:25-68).  Design differences: one WARP (not one
+// CTA) owns a (batch, channel) sequence, so tiny-L / huge-batch*dim shapes (XFMamba's stage 3/4 and fusion blocks)
+// fill the machine; the scan over L is a chunked warp-shuffle scan of affine maps with the state carried in a
+// register; only h (not (a-product, h)) is checkpointed per chunk.
+//
+// This is the drop-in for `selective_scan_fn`; the SS2D hot path uses the fused kernels in ss2d_fused.cu instead.
+#include "xfscan_common.cuh"
+
+namespace xfs {
+
+constexpr int kWarpsPerCta = 4;
+constexpr int kMaxState = 256;   // selective_scan.cpp:199
+
+// ---------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, typename TO>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+sscan_fwd_kernel(const xfs_scan_fwd_args p) {
+    __shared__ float s_h[kWarpsPerCta][kMaxState];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t seq = (int64_t)blockIdx.x * kWarpsPerCta + wib;      // b*dim + d
+    if (seq >= p.batch * p.dim) return;
+    const int64_t b = seq / p.dim, d = seq % p.dim;
+    const int64_t L = p.seqlen, N = p.dstate;
+    const int64_t g = d / (p.dim / p.ngroups);
+    const int64_t nchunks = (L + kChunk - 1) / kChunk;
+
+    const T* __restrict__ u_row = reinterpret_cast<const T*>(p.u) + seq * L;
+    const T* __restrict__ dt_row = reinterpret_cast<const T*>(p.delta) + seq * L;
+    const T* __restrict__ Bg = reinterpret_cast<const T*>(p.B) + (b * p.ngroups + g) * N * L;
+    const T* __restrict__ Cg = reinterpret_cast<const T*>(p.C) + (b * p.ngroups + g) * N * L;
+    TO* __restrict__ o_row = reinterpret_cast<TO*>(p.out) + seq * L;
+    const bool vin = row_vec_ok(reinterpret_cast<const T*>(p.u), L) && row_vec_ok(reinterpret_cast<const T*>(p.delta), L) &&
+                     row_vec_ok(reinterpret_cast<const T*>(p.B), L) && row_vec_ok(reinterpret_cast<const T*>(p.C), L);
+    const bool vout = row_vec_ok(reinterpret_cast<const TO*>(p.out), L);
+    const float bias = p.delta_bias ? p.delta_bias[d] : 0.0f;
+    const float Dd = p.D ? p.D[d] : 0.0f;
+    float* __restrict__ st = p.states ? p.states + seq * nchunks * N : nullptr;
+
+    for (int n = lane; n < N; n += 32) s_h[wib][n] = 0.0f;
+    __syncwarp();
+
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int64_t l0 = c * kChunk + lane * kItems;
+        float dt[8], u[8], y[8];
+        load8(dt_row, l0, L, vin, dt);
+        load8(u_row, l0, L, vin, u);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float x = dt[i] + bias, e;
+            dt[i] = p.delta_softplus ? softplus_fwd(x, e) : x;
+            if (l0 + i >= L) dt[i] = 0.0f;          // identity map beyond the end of the sequence
+            y[i] = Dd * u[i];
+        }
+        for (int64_t n = 0; n < N; ++n) {
+            const float A2 = p.A[d * N + n] * kLog2e;
+            float Bv[8], Cv[8], S[8], P[8];
+            load8(Bg + n * L, l0, L, vin, Bv);
+            load8(Cg + n * L, l0, L, vin, Cv);
+            float Pr = 1.0f, Sr = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float a = ex2(dt[i] * A2);
+                const float bu = (dt[i] * Bv[i]) * u[i];
+                Sr = fmaf(a, Sr, bu);
+                Pr *= a;
+                S[i] = Sr;
+                P[i] = Pr;
+            }
+            float h_out;
+            const float h_in = warp_prefix<false>(Pr, Sr, s_h[wib][n], lane, h_out);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) y[i] = fmaf(Cv[i], fmaf(P[i], h_in, S[i]), y[i]);
+            __syncwarp();
+            if (lane == 0) {
+                s_h[wib][n] = h_out;
+                if (st) st[c * N + n] = h_out;
+            }
+        }
+        __syncwarp();
+        store8(o_row, l0, L, vout, y);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward.  Chunks are walked last -> first.  Per chunk and state n:
+//   forward re-scan from the checkpointed state entering the chunk          -> h_i
+//   reverse scan of q_i = a_i * (C_i dy_i + q_{i+1})                        -> g_i = C_i dy_i + q_{i+1}  (= dL/dh_i)
+//   du += g dt B;  ddt += g (B u + A (h - b));  dA += g dt (h - b);  dB += g dt u;  dC += dy h   (b = dt B u)
+// dB / dC are shared by every channel of a group -> fp32 atomics (as the reference does, bwd_kernel.cuh:221-227).
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, typename TDO>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+sscan_bwd_kernel(const xfs_scan_bwd_args p) {
+    __shared__ float s_q[kWarpsPerCta][kMaxState];    // reverse carry per state
+    __shared__ float s_dA[kWarpsPerCta][kMaxState];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t seq = (int64_t)blockIdx.x * kWarpsPerCta + wib;
+    if (seq >= p.batch * p.dim) return;
+    const int64_t b = seq / p.dim, d = seq % p.dim;
+    const int64_t L = p.seqlen, N = p.dstate;
+    const int64_t g = d / (p.dim / p.ngroups);
+    const int64_t nchunks = (L + kChunk - 1) / kChunk;
+
+    const T* __restrict__ u_row = reinterpret_cast<const T*>(p.u) + seq * L;
+    const T* __restrict__ dt_row = reinterpret_cast<const T*>(p.delta) + seq * L;
+    const TDO* __restrict__ dy_row = reinterpret_cast<const TDO*>(p.dout) + seq * L;
+    const T* __restrict__ Bg = reinterpret_cast<const T*>(p.B) + (b * p.ngroups + g) * N * L;
+    const T* __restrict__ Cg = reinterpret_cast<const T*>(p.C) + (b * p.ngroups + g) * N * L;
+    float* __restrict__ dBg = p.dB + (b * p.ngroups + g) * N * L;
+    float* __restrict__ dCg = p.dC + (b * p.ngroups + g) * N * L;
+    T* __restrict__ du_row = reinterpret_cast<T*>(p.du) + seq * L;
+    T* __restrict__ ddt_row = reinterpret_cast<T*>(p.ddelta) + seq * L;
+    const bool vin = row_vec_ok(reinterpret_cast<const T*>(p.u), L) && row_vec_ok(reinterpret_cast<const T*>(p.delta), L) &&
+                     row_vec_ok(reinterpret_cast<const T*>(p.B), L) && row_vec_ok(reinterpret_cast<const T*>(p.C), L);
+    const bool vdy = row_vec_ok(reinterpret_cast<const TDO*>(p.dout), L);
+    const bool vout = row_vec_ok(reinterpret_cast<const T*>(p.du), L) && row_vec_ok(reinterpret_cast<const T*>(p.ddelta), L);
+    const float bias = p.delta_bias ? p.delta_bias[d] : 0.0f;
+    const float Dd = p.D ? p.D[d] : 0.0f;
+    const float* __restrict__ st = p.states + seq * nchunks * N;
+
+    for (int n = lane; n < N; n += 32) { s_q[wib][n] = 0.0f; s_dA[wib][n] = 0.0f; }
+    __syncwarp();
+    float dD_acc = 0.0f, dbias_acc = 0.0f;
+
+    for (int64_t c = nchunks - 1; c >= 0; --c) {
+        const int64_t l0 = c * kChunk + lane * kItems;
+        float dt[8], u[8], dy[8], sig[8], du[8], ddt[8];
+        load8(dt_row, l0, L, vin, dt);
+        load8(u_row, l0, L, vin, u);
+        load8(dy_row, l0, L, vdy, dy);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float x = dt[i] + bias;
+            float e = 0.0f;
+            dt[i] = p.delta_softplus ? softplus_fwd(x, e) : x;
+            sig[i] = p.delta_softplus ? ((x > 20.0f) ? 1.0f : e * rcp(1.0f + e)) : 1.0f;
+            if (l0 + i >= L) dt[i] = 0.0f;
+            du[i] = Dd * dy[i];
+            ddt[i] = 0.0f;
+            dD_acc = fmaf(dy[i], u[i], dD_acc);
+        }
+        for (int64_t n = 0; n < N; ++n) {
+            const float An = p.A[d * N + n];
+            const float A2 = An * kLog2e;
+            float Bv[8], Cv[8], a[8], bu[8], S[8], P[8];
+            load8(Bg + n * L, l0, L, vin, Bv);
+            load8(Cg + n * L, l0, L, vin, Cv);
+            float Pr = 1.0f, Sr = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                a[i] = ex2(dt[i] * A2);
+                bu[i] = (dt[i] * Bv[i]) * u[i];
+                Sr = fmaf(a[i], Sr, bu[i]);
+                Pr *= a[i];
+                S[i] = Sr;
+                P[i] = Pr;
+            }
+            float unused;
+            const float h_start = (c > 0) ? st[(c - 1) * N + n] : 0.0f;
+            const float h_in = warp_prefix<false>(Pr, Sr, h_start, lane, unused);
+            // reverse scan of the maps q -> a_i*q + a_i*C_i*dy_i, walking i = 7..0 and lanes 31..0
+            float Sq[8], Pq[8];
+            Pr = 1.0f;
+            Sr = 0.0f;
+#pragma unroll
+            for (int i = 7; i >= 0; --i) {
+                const float cd = Cv[i] * dy[i];
+                Sr = a[i] * (Sr + cd);
+                Pr *= a[i];
+                Sq[i] = Sr;
+                Pq[i] = Pr;
+            }
+            float q_out;
+            const float q_in = warp_prefix<true>(Pr, Sr, s_q[wib][n], lane, q_out);
+            float dA_part = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float h = fmaf(P[i], h_in, S[i]);
+                const float q_next = (i == 7) ? q_in : fmaf(Pq[i == 7 ? 7 : i + 1], q_in, Sq[i == 7 ? 7 : i + 1]);
+                const float gi = fmaf(Cv[i], dy[i], q_next);
+                const float hp = h - bu[i];                       // a_i * h_{i-1}
+                du[i] = fmaf(gi * dt[i], Bv[i], du[i]);
+                ddt[i] = fmaf(gi, fmaf(Bv[i], u[i], An * hp), ddt[i]);
+                dA_part = fmaf(gi * dt[i], hp, dA_part);
+                if (l0 + i < L) {
+                    atomicAdd(dBg + n * L + l0 + i, gi * dt[i] * u[i]);
+                    atomicAdd(dCg + n * L + l0 + i, dy[i] * h);
+                }
+            }
+            dA_part = warp_sum(dA_part);
+            __syncwarp();
+            if (lane == 0) {
+                s_q[wib][n] = q_out;
+                s_dA[wib][n] += dA_part;
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            ddt[i] *= sig[i];
+            if (l0 + i < L) dbias_acc += ddt[i];
+        }
+        store8(du_row, l0, L, vout, du);
+        store8(ddt_row, l0, L, vout, ddt);
+    }
+    __syncwarp();
+    for (int n = lane; n < N; n += 32) atomicAdd(p.dA + d * N + n, s_dA[wib][n]);
+    dD_acc = warp_sum(dD_acc);
+    dbias_acc = warp_sum(dbias_acc);
+    if (lane == 0) {
+        if (p.dD) atomicAdd(p.dD + d, dD_acc);
+        if (p.ddelta_bias) atomicAdd(p.ddelta_bias + d, dbias_acc);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+static int launch_fwd_t(const xfs_scan_fwd_args& a, cudaStream_t st) {
+    const int64_t nseq = a.batch * a.dim;
+    const unsigned grid = (unsigned)((nseq + kWarpsPerCta - 1) / kWarpsPerCta);
+    if (a.out_dtype == XFS_F32)
+        sscan_fwd_kernel<T, float><<<grid, kWarpsPerCta * 32, 0, st>>>(a);
+    else
+        sscan_fwd_kernel<T, T><<<grid, kWarpsPerCta * 32, 0, st>>>(a);
+    return check_launch();
+}
+
+int launch_scan_fwd(const xfs_scan_fwd_args& a, cudaStream_t st) {
+    switch (a.dtype) {
+        case XFS_F32: return launch_fwd_t<float>(a, st);
+        case XFS_BF16: return launch_fwd_t<__nv_bfloat16>(a, st);
+        default: return launch_fwd_t<__half>(a, st);
+    }
+}
+
+template <typename T>
+static int launch_bwd_t(const xfs_scan_bwd_args& a, cudaStream_t st) {
+    const int64_t nseq = a.batch * a.dim;
+    const unsigned grid = (unsigned)((nseq + kWarpsPerCta - 1) / kWarpsPerCta);
+    if (a.dout_dtype == XFS_F32)
+        sscan_bwd_kernel<T, float><<<grid, kWarpsPerCta * 32, 0, st>>>(a);
+    else
+        sscan_bwd_kernel<T, T><<<grid, kWarpsPerCta * 32, 0, st>>>(a);
+    return check_launch();
+}
+
+int launch_scan_bwd(const xfs_scan_bwd_args& a, cudaStream_t st) {
+    switch (a.dtype) {
+        case XFS_F32: return launch_bwd_t<float>(a, st);
+        case XFS_BF16: return launch_bwd_t<__nv_bfloat16>(a, st);
+        default: return launch_bwd_t<__half>(a, st);
+    }
+}
+
+}  // namespace xfs

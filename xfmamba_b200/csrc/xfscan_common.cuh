@@ -1,0 +1,173 @@
+// xfscan_common.cuh -- device helpers shared by the sm_100a scan kernels.
+//
+// Vocabulary (follows the reference): a *sequence* is one (batch, channel) row of length L; a *chunk* is the
+// kChunk positions one warp scans per step (32 lanes x kItems consecutive positions); the *state* h is the S6
+// recurrence value carried from chunk to chunk; a *route* is one of the 4 CrossScan orders.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/xfscan.h"
+
+namespace xfs {
+
+constexpr int kItems = 8;              // consecutive positions per lane
+constexpr int kChunk = 32 * kItems;    // positions per warp step (== xfs_chunk_len())
+constexpr unsigned kFull = 0xffffffffu;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+int check_launch();   // counts the launch (xfs_launch_count) and returns cudaGetLastError(); defined in capi.cu
+
+// ---------------------------------------------------------------------------------------------------------
+// transcendental primitives: one MUFU each
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// softplus with torch semantics (beta=1, threshold=20; models/csms6s.py:49-50): x > 20 ? x : log1p(exp(x)).
+// MUFU.LG2 has ~2^-22 ABSOLUTE error near 1, which is a large RELATIVE error of log1p(e) when e is small -- and
+// small e (dt in [1e-3, 1e-1]) is exactly the regime Mamba's dt_bias init puts the model in
+// (models/fusion_vmamba.py:303-310).  So below 2^-6 the alternating series is used instead (truncation < 2e-8 rel).
+// `e_out` returns exp(x) for the backward's sigmoid.
+__device__ __forceinline__ float softplus_fwd(float x, float& e_out) {
+    const float e = ex2(x * kLog2e);
+    e_out = e;
+    const float big = lg2(1.0f + e) * kLn2;
+    const float ser = e * fmaf(e, fmaf(e, fmaf(e, -0.25f, 0.33333334f), -0.5f), 1.0f);
+    const float r = (e < 0.015625f) ? ser : big;
+    return (x > 20.0f) ? x : r;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// element type traits: 8 consecutive elements <-> 8 floats
+// ---------------------------------------------------------------------------------------------------------
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+    static constexpr int kVec = 4;  // elements per 16-byte vector
+    static __device__ __forceinline__ float to_f(float v) { return v; }
+    static __device__ __forceinline__ float from_f(float v) { return v; }
+};
+template <> struct Elem<__nv_bfloat16> {
+    static constexpr int kVec = 8;
+    static __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+    static __device__ __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+};
+template <> struct Elem<__half> {
+    static constexpr int kVec = 8;
+    static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+    static __device__ __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
+};
+
+// Streaming 16-byte global accesses.  Loads keep the default L1 policy on purpose: a lane's two vectors of a
+// chunk share 32-byte sectors with its neighbours', the second access is an L1 hit.
+__device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+__device__ __forceinline__ void stg16(void* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
+
+// Load elements [l0, l0+8) of a row of length L into v (positions >= L or < 0 get `fill`).  `vec_ok` says the row
+// base is 16-byte aligned and L is a multiple of the vector width, so any in-range aligned group may be vector loaded.
+template <typename T>
+__device__ __forceinline__ void load8(const T* __restrict__ row, int64_t l0, int64_t L, bool vec_ok, float (&v)[8],
+                                      float fill = 0.0f) {
+    if (vec_ok && l0 >= 0 && l0 + 8 <= L) {
+        if constexpr (Elem<T>::kVec == 4) {
+            const uint4 a = ldg16(row + l0), b = ldg16(row + l0 + 4);
+            v[0] = __uint_as_float(a.x); v[1] = __uint_as_float(a.y); v[2] = __uint_as_float(a.z); v[3] = __uint_as_float(a.w);
+            v[4] = __uint_as_float(b.x); v[5] = __uint_as_float(b.y); v[6] = __uint_as_float(b.z); v[7] = __uint_as_float(b.w);
+        } else {
+            const uint4 a = ldg16(row + l0);
+            const T* e = reinterpret_cast<const T*>(&a);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = Elem<T>::to_f(e[i]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t l = l0 + i;
+            v[i] = (l >= 0 && l < L) ? Elem<T>::to_f(row[l]) : fill;
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void store8(T* __restrict__ row, int64_t l0, int64_t L, bool vec_ok, const float (&v)[8]) {
+    if (vec_ok && l0 >= 0 && l0 + 8 <= L) {
+        if constexpr (Elem<T>::kVec == 4) {
+            stg16(row + l0, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));
+            stg16(row + l0 + 4, make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
+        } else {
+            uint4 a;
+            T* e = reinterpret_cast<T*>(&a);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) e[i] = Elem<T>::from_f(v[i]);
+            stg16(row + l0, a);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t l = l0 + i;
+            if (l >= 0 && l < L) row[l] = Elem<T>::from_f(v[i]);
+        }
+    }
+}
+
+template <typename T> __device__ __forceinline__ bool row_vec_ok(const T* base, int64_t L) {
+    return (L % Elem<T>::kVec == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+}
+
+__device__ __forceinline__ void reverse8(float (&v)[8]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float t = v[i]; v[i] = v[7 - i]; v[7 - i] = t; }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// chunked warp-shuffle scan of the affine maps  h -> a*h + b.
+//
+// Each lane first folds its kItems maps sequentially into (P, S) = (prod a, value of the fold started at 0).
+// warp_prefix then turns the per-lane folds into, for every lane, the state ENTERING that lane given the state
+// `carry` entering the chunk, and returns the state leaving the chunk (lane-uniform).  kRev walks lanes 31 -> 0.
+// 5 steps x (2 SHFL + FMUL + FFMA + 2 SEL).
+// ---------------------------------------------------------------------------------------------------------
+template <bool kRev>
+__device__ __forceinline__ float warp_prefix(float P, float S, float carry, int lane, float& chunk_out) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        float Pn = kRev ? __shfl_down_sync(kFull, P, off) : __shfl_up_sync(kFull, P, off);
+        float Sn = kRev ? __shfl_down_sync(kFull, S, off) : __shfl_up_sync(kFull, S, off);
+        const bool has = kRev ? (lane + off < 32) : (lane >= off);
+        Pn = has ? Pn : 1.0f;
+        Sn = has ? Sn : 0.0f;
+        S = fmaf(P, Sn, S);   // apply the earlier maps first, then this lane's
+        P = P * Pn;
+    }
+    // (P, S) is now the inclusive fold up to and including this lane
+    const float incl = fmaf(P, carry, S);
+    chunk_out = __shfl_sync(kFull, incl, kRev ? 0 : 31);
+    float prev = kRev ? __shfl_down_sync(kFull, incl, 1) : __shfl_up_sync(kFull, incl, 1);
+    const bool first = kRev ? (lane == 31) : (lane == 0);
+    return first ? carry : prev;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
+    return v;
+}
+
+}  // namespace xfs

@@ -1,0 +1,216 @@
+"""Cross-view fusion scans and the fused SS2D core.
+
+* ``SwappingScan_multiview`` / ``SwappingMerge_multiview`` -- drop-ins for ``models/fusion_vmamba.py:189-241`` (the
+  reference builds a boolean mask on the CPU and runs ~8 index kernels; here it is one copy kernel).  The backward
+  passes follow the reference AS WRITTEN: ``SwappingScan_multiview.backward`` returns ``ys[:,0], ys[:,1]`` without
+  un-swapping the even channels (``:217-221``), so gradients of even channels reach the *other* view.  Parity with
+  the reference is the contract; ``exact_adjoint=True`` on ``swapping_scan`` gives the mathematically exact adjoint.
+* ``ss2d_scan`` -- NEW fused entry point: ``cross_merge(selective_scan(cross_scan(x), ...))`` of
+  ``SS2Dv2.forward_corev2`` (``models/fusion_vmamba.py:1145,1170-1174``) as ONE forward kernel and ONE backward kernel
+  (csrc/ss2d_fused.cu).  When the per-channel working set does not fit shared memory it composes the three
+  stand-alone CUDA operators instead (still no CPU path).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .csm import cross_merge_raw, cross_scan_raw
+from .csms6s import _check_scan_args, selective_scan_bwd_raw, selective_scan_fwd_raw
+
+__all__ = ["SwappingScan_multiview", "SwappingMerge_multiview", "swapping_scan", "swapping_merge", "ss2d_scan",
+           "SS2DScanFn", "ss2d_fused_supported"]
+
+
+def _swap_call(fn_name, a, b, outs, B, C, L, dev):
+    fn = getattr(_lib.lib(), fn_name)
+    with torch.cuda.device(dev):
+        rc = fn(_lib.ptr(a), _lib.ptr(b) if b is not None else _lib.ptr(outs[0]),
+                _lib.ptr(outs[0]) if b is not None else _lib.ptr(outs[1]), B, C, L, _lib.dtype_code(a), _lib.stream(dev))
+    _lib.check(rc, fn_name)
+
+
+def _swap_scan_raw(x, x2):
+    dev = _lib.require_cuda(x, x2)
+    if x.shape != x2.shape or x.dtype != x2.dtype:
+        raise RuntimeError(f"SwappingScan: the two views must match; got {tuple(x.shape)}/{x.dtype} vs {tuple(x2.shape)}/{x2.dtype}")
+    B, C = x.shape[:2]
+    L = x[0, 0].numel()
+    x, x2 = x.contiguous(), x2.contiguous()
+    out = torch.empty((B, 2, C, L), dtype=x.dtype, device=dev)
+    if out.numel():
+        with torch.cuda.device(dev):
+            rc = _lib.lib().xfs_swap_scan(_lib.ptr(x), _lib.ptr(x2), _lib.ptr(out), B, C, L, _lib.dtype_code(x), _lib.stream(dev))
+        _lib.check(rc, "swap_scan")
+    return out
+
+
+def _swap_merge_raw(ys):
+    dev = _lib.require_cuda(ys)
+    B, K, C, L = ys.shape
+    if K != 2:
+        raise RuntimeError(f"SwappingMerge expects (B, 2, C, L); got {tuple(ys.shape)}")
+    ys = ys.contiguous()
+    y = torch.empty((B, C, L), dtype=ys.dtype, device=dev)
+    y2 = torch.empty_like(y)
+    if y.numel():
+        with torch.cuda.device(dev):
+            rc = _lib.lib().xfs_swap_merge(_lib.ptr(ys), _lib.ptr(y), _lib.ptr(y2), B, C, L, _lib.dtype_code(ys), _lib.stream(dev))
+        _lib.check(rc, "swap_merge")
+    return y, y2
+
+
+def _swap_stack_raw(y, y2):
+    dev = _lib.require_cuda(y, y2)
+    B, C, L = y.shape
+    y, y2 = y.contiguous(), y2.contiguous()
+    ys = torch.empty((B, 2, C, L), dtype=y.dtype, device=dev)
+    if ys.numel():
+        with torch.cuda.device(dev):
+            rc = _lib.lib().xfs_swap_stack(_lib.ptr(y), _lib.ptr(y2), _lib.ptr(ys), B, C, L, _lib.dtype_code(y), _lib.stream(dev))
+        _lib.check(rc, "swap_stack")
+    return ys
+
+
+class SwappingScan_multiview(torch.autograd.Function):
+    """models/fusion_vmamba.py:189-221"""
+
+    @staticmethod
+    def forward(ctx, x: torch.Tensor, x2: torch.Tensor, exact_adjoint: bool = False):
+        B, C, H, W = x.shape
+        ctx.shape = (B, C, H, W)
+        ctx.exact_adjoint = exact_adjoint
+        return _swap_scan_raw(x, x2)
+
+    @staticmethod
+    def backward(ctx, ys: torch.Tensor):
+        B, C, H, W = ctx.shape
+        if ctx.exact_adjoint:
+            # the swap is an involution on (view, even channel): its adjoint is the same swap of the two grad halves
+            g = _swap_scan_raw(ys[:, 0], ys[:, 1])
+            return g[:, 0].reshape(B, C, H, W), g[:, 1].reshape(B, C, H, W), None
+        # reference behaviour: plain split (models/fusion_vmamba.py:217-221)
+        return ys[:, 0].reshape(B, -1, H, W), ys[:, 1].reshape(B, -1, H, W), None
+
+
+class SwappingMerge_multiview(torch.autograd.Function):
+    """models/fusion_vmamba.py:224-241"""
+
+    @staticmethod
+    def forward(ctx, ys: torch.Tensor):
+        return _swap_merge_raw(ys)
+
+    @staticmethod
+    def backward(ctx, x: torch.Tensor, x2: torch.Tensor):
+        return _swap_stack_raw(x, x2)
+
+
+def swapping_scan(x, x2, exact_adjoint=False):
+    return SwappingScan_multiview.apply(x, x2, exact_adjoint)
+
+
+def swapping_merge(ys):
+    return SwappingMerge_multiview.apply(ys)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fused SS2D core
+# ------------------------------------------------------------------------------------------------------------------
+def ss2d_fused_supported(D: int, N: int, H: int, W: int, dtype: torch.dtype, backward: bool = False) -> bool:
+    return bool(_lib.lib().xfs_ss2d_supported(D, N, H, W, _lib._DTYPES[dtype], int(backward)))
+
+
+class SS2DScanFn(torch.autograd.Function):
+    """y = cross_merge(selective_scan(cross_scan(x), delta, A, Bs, Cs, Ds, delta_bias)), all four routes in one kernel."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, x, delta, A, Bs, Cs, Ds, delta_bias, delta_softplus, oflex):
+        if x.dim() != 4:
+            raise RuntimeError(f"ss2d_scan: x must be (B, D, H, W); got {tuple(x.shape)}")
+        Bsz, D, H, W = x.shape
+        L = H * W
+        delta = delta.reshape(Bsz, 4 * D, L)
+        if x.dtype != delta.dtype:
+            raise RuntimeError(f"ss2d_scan: x ({x.dtype}) and delta ({delta.dtype}) must share one dtype")
+        dev, Bs, Cs, _, _, _, G, N = _check_scan_args(delta, delta, A, Bs, Cs, Ds, delta_bias)
+        _lib.require_cuda(x)
+        if G != 4:
+            raise RuntimeError(f"ss2d_scan: Bs/Cs must be (B, 4, N, L); got {tuple(Bs.shape)}")
+        need = any(ctx.needs_input_grad)
+        fused = ss2d_fused_supported(D, N, H, W, x.dtype, False) and (not need or ss2d_fused_supported(D, N, H, W, x.dtype, True))
+        x, delta, A, Bs, Cs = (t.contiguous() for t in (x, delta, A, Bs, Cs))
+        Ds = None if Ds is None else Ds.contiguous()
+        delta_bias = None if delta_bias is None else delta_bias.contiguous()
+        out_dtype = torch.float32 if oflex else x.dtype
+        if fused:
+            y = torch.empty((Bsz, D, L), dtype=out_dtype, device=dev)
+            states = torch.empty((Bsz, 4 * D, _lib.num_chunks(L), N), dtype=torch.float32, device=dev) if need else None
+            if y.numel():
+                args = _lib.Ss2dFwdArgs(_lib.ptr(x), _lib.ptr(delta), _lib.ptr(A), _lib.ptr(Bs), _lib.ptr(Cs), _lib.ptr(Ds),
+                                        _lib.ptr(delta_bias), _lib.ptr(y), _lib.ptr(states), Bsz, D, N, H, W,
+                                        _lib.dtype_code(x), _lib.dtype_code(y), int(bool(delta_softplus)), 0)
+                with torch.cuda.device(dev):
+                    rc = _lib.lib().xfs_ss2d_fwd(args, _lib.stream(dev))
+                _lib.check(rc, "ss2d_fwd")
+        else:
+            xs = cross_scan_raw(x).view(Bsz, 4 * D, L)
+            ys, states, _ = selective_scan_fwd_raw(xs, delta, A, Bs, Cs, Ds, delta_bias, delta_softplus, oflex, need_states=need)
+            y = cross_merge_raw(ys.view(Bsz, 4, D, L), H, W)
+        if need:
+            ctx.fused, ctx.delta_softplus = fused, delta_softplus
+            ctx.has_D, ctx.has_bias = Ds is not None, delta_bias is not None
+            ctx.save_for_backward(*[t for t in (x, delta, A, Bs, Cs, Ds, delta_bias) if t is not None], states)
+        return y
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        saved = list(ctx.saved_tensors)
+        states = saved.pop()
+        x, delta, A, Bs, Cs = saved[:5]
+        rest = saved[5:]
+        Ds = rest.pop(0) if ctx.has_D else None
+        delta_bias = rest.pop(0) if ctx.has_bias else None
+        Bsz, D, H, W = x.shape
+        L = H * W
+        N = Bs.shape[2]
+        dev = x.device
+        dy = dy.contiguous()
+        if dy.dtype not in (torch.float32, x.dtype):
+            dy = dy.to(x.dtype)
+        if ctx.fused:
+            dx = torch.empty_like(x)
+            ddelta = torch.empty_like(delta)
+            dA = torch.zeros_like(A)
+            dBs = torch.zeros(Bs.shape, dtype=torch.float32, device=dev)
+            dCs = torch.zeros(Cs.shape, dtype=torch.float32, device=dev)
+            dDs = None if Ds is None else torch.zeros_like(Ds)
+            dbias = None if delta_bias is None else torch.zeros_like(delta_bias)
+            if x.numel():
+                args = _lib.Ss2dBwdArgs(_lib.ptr(x), _lib.ptr(delta), _lib.ptr(A), _lib.ptr(Bs), _lib.ptr(Cs), _lib.ptr(Ds),
+                                        _lib.ptr(delta_bias), _lib.ptr(dy), _lib.ptr(states), _lib.ptr(dx), _lib.ptr(ddelta),
+                                        _lib.ptr(dA), _lib.ptr(dBs), _lib.ptr(dCs), _lib.ptr(dDs), _lib.ptr(dbias),
+                                        Bsz, D, N, H, W, _lib.dtype_code(x), _lib.dtype_code(dy), int(bool(ctx.delta_softplus)), 0)
+                with torch.cuda.device(dev):
+                    rc = _lib.lib().xfs_ss2d_bwd(args, _lib.stream(dev))
+                _lib.check(rc, "ss2d_bwd")
+            dBs, dCs = dBs.to(Bs.dtype), dCs.to(Cs.dtype)
+        else:
+            xs = cross_scan_raw(x).view(Bsz, 4 * D, L)
+            dys = cross_scan_raw(dy.view(Bsz, D, H, W)).view(Bsz, 4 * D, L)
+            du, ddelta, dA, dBs, dCs, dDs, dbias = selective_scan_bwd_raw(xs, delta, A, Bs, Cs, Ds, delta_bias, dys, states,
+                                                                          ctx.delta_softplus)
+            dx = cross_merge_raw(du.view(Bsz, 4, D, L), H, W).view(Bsz, D, H, W)
+        return dx, ddelta, dA, dBs, dCs, dDs, dbias, None, None
+
+
+def ss2d_scan(x, delta, A, Bs, Cs, Ds=None, delta_bias=None, delta_softplus=True, oflex=True):
+    """Fused SS2D core.
+
+    x (B, D, H, W); delta (B, 4*D, H*W) or (B, 4, D, H*W) -- the dt_proj output, in the scan order of each route;
+    A (4*D, N) f32; Bs, Cs (B, 4, N, H*W) in scan order; Ds, delta_bias (4*D) f32.  Returns y (B, D, H*W) in spatial
+    order: f32 when ``oflex`` else x.dtype -- exactly ``cross_merge_fn(selective_scan_fn(cross_scan_fn(x).view(B,-1,L),
+    delta, A, Bs, Cs, Ds, delta_bias, delta_softplus, oflex).view(B,4,-1,H,W))``.
+    """
+    return SS2DScanFn.apply(x, delta, A, Bs, Cs, Ds, delta_bias, delta_softplus, oflex)
