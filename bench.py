@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- the SS2D hot path on B200: `python bench.py --gpus N --steps K --warmup W [--impl reference]`.
+
+Workload (BASELINE.json configs[1]): the SS2D core at VMamba stage-1 shape -- 56x56 tokens, d_inner 192, d_state 1,
+K=4 routes -- forward + backward, on a synthetic batch of 64 images (= 32 two-view pairs) per GPU.  One "step" is one
+fused forward kernel + one fused backward kernel over that batch (plus the zero-fills the backward needs).  At N > 1
+GPUs every rank runs the same per-GPU batch (weak scaling, batch sharded) and the parameter gradients
+(dA, dDs, ddelta_bias) are all-reduced with NCCL each step -- the only exchange the path has.
+
+The JSON line carries: value (pairs/s, inputs resident in HBM), e2e (same step through the public autograd API with
+pinned HOST buffers: H2D of every input + D2H of a scalar each step), roofline of the dominant kernel (fused backward)
+and of the forward (CUDA-event time of each launch inside the timed region vs MEASURED_PEAKS.json), cpu_baseline (the
+CPU oracle port timed on this box's host cores, rank 0, N=1 only), clocks sampled during the timed region, and the
+number of kernels launched (counted by the library).
+
+`--impl reference` times the reference arm: the CPU restatement of the reference's algorithm for this path
+(oracle/, OpenMP over all host cores; the reference itself is Python and does not exist on the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(name="ss2d_stage1_fwd_bwd", H=56, W=56, D=192, N=1, K=4)
+FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def alg_bytes(batch, D, N, L, s, s_o=4, K=4):
+    """SURVEY.md 8(d) / BASELINE.md section 5: algorithmic HBM bytes of one launch"""
+    fwd = batch * L * (D * s + K * D * s + 2 * K * N * s + D * s_o) + K * D * (N + 2) * 4
+    bwd = batch * L * (2 * D * s + 2 * K * D * s + 4 * K * N * s + D * s_o)
+    return fwd, bwd
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def traffic_from_profiles(kernel):
+    """dram bytes per launch from the committed ncu summary, if any (profiles/traffic.json)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(kernel)
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """samples SM clock and throttle reasons through NVML while the timed region runs"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap", nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=1.0)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def synth_inputs_np(batch, seed=0):
+    import numpy as np
+    w = WORKLOAD
+    L = w["H"] * w["W"]
+    rng = np.random.default_rng(seed)
+    f = lambda *s: rng.standard_normal(s, dtype=np.float32)
+    r = lambda *s: rng.random(s, dtype=np.float32)
+    KD = w["K"] * w["D"]
+    # distributions of the reference's own scan test (models/selective_scan/test_selective_scan.py:157-179)
+    return dict(x=f(batch, w["D"], w["H"], w["W"]), delta=0.5 * r(batch, KD, L), A=-0.5 * r(KD, w["N"]),
+                Bs=f(batch, w["K"], w["N"], L), Cs=f(batch, w["K"], w["N"], L), Ds=f(KD), delta_bias=0.5 * r(KD),
+                dy=f(batch, w["D"], L))
+
+
+def cpu_baseline(sample_batch, reps=1):
+    """fwd+bwd of the same path with the CPU oracle (C, OpenMP) on `sample_batch` images; returns pairs/s"""
+    import oracle
+    c = synth_inputs_np(sample_batch, seed=1)
+    keys = ["x", "delta", "A", "Bs", "Cs", "Ds", "delta_bias"]
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        oracle.ss2d_fwd(*[c[k] for k in keys], True, "f32")
+        oracle.ss2d_bwd(*[c[k] for k in keys], c["dy"], True, "f32")
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return (sample_batch / 2) / best, best
+
+
+def run_reference(args):
+    """reference arm: CPU restatement (oracle port) on the host cores; rank 0 only"""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    sample = 4                                   # images per step (2 two-view pairs), same shape as the GPU workload
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(sample)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_baseline(sample)
+    dt = time.perf_counter() - t0
+    value = (sample / 2) * args.steps / dt
+    w = WORKLOAD
+    line = {"impl": "reference", "metric": "two_view_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["name"], "H": w["H"], "W": w["W"], "d_inner": w["D"], "d_state": w["N"], "K": w["K"],
+                       "images_per_step": sample},
+            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample} images (2 pairs) per step, SS2D core fwd+bwd, oracle/ C port with OpenMP"},
+            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from xfmamba_b200 import _lib, fusion_ops, ss2d_scan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    rc = _lib.lib().xfs_device_ok(local)
+    assert rc == 0, _lib.lib().xfs_error_string(rc).decode()
+
+    w = WORKLOAD
+    batch, L = args.batch, w["H"] * w["W"]
+    tdt = {"f32": torch.float32, "bf16": torch.bfloat16}[args.dtype]
+    s = 4 if args.dtype == "f32" else 2
+    host = {k: torch.from_numpy(v) for k, v in synth_inputs_np(batch, seed=rank).items()}
+    cast = lambda k, v: v.to(tdt) if k in ("x", "delta", "Bs", "Cs") else v
+    d = {k: cast(k, v).to(dev) for k, v in host.items()}
+    keys = ["x", "delta", "A", "Bs", "Cs", "Ds", "delta_bias"]
+
+    # reusable output buffers (device-resident leg)
+    y = torch.empty((batch, w["D"], L), dtype=torch.float32, device=dev)
+    states = torch.empty((batch, 4 * w["D"], _lib.num_chunks(L), w["N"]), dtype=torch.float32, device=dev)
+    grads = (torch.empty_like(d["x"]), torch.empty_like(d["delta"]), torch.empty_like(d["A"]),
+             torch.empty(d["Bs"].shape, dtype=torch.float32, device=dev), torch.empty(d["Cs"].shape, dtype=torch.float32, device=dev),
+             torch.empty_like(d["Ds"]), torch.empty_like(d["delta_bias"]))
+    flat = torch.empty(d["A"].numel() + d["Ds"].numel() + d["delta_bias"].numel(), dtype=torch.float32, device=dev)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    fwd_ev, bwd_ev = [], []
+
+    def step(timed):
+        e0, e1, e2, e1b = (ev(), ev(), ev(), ev()) if timed else (None, None, None, None)
+        if timed:
+            e0.record()
+        fusion_ops.ss2d_fwd_raw(*[d[k] for k in keys], True, torch.float32, True, y, states)
+        if timed:
+            e1.record()
+        # zero-fills of the accumulated gradients are part of the step but not of the kernel's event bracket
+        for acc in (grads[2], grads[3], grads[4], grads[5], grads[6]):
+            acc.zero_()
+        if timed:
+            e1b.record()
+        fusion_ops.ss2d_bwd_raw(*[d[k] for k in keys], d["dy"], states, True, grads, zero=False)
+        if timed:
+            e2.record()
+            fwd_ev.append((e0, e1))
+            bwd_ev.append((e1b, e2))
+        if world > 1:   # data-parallel exchange of the parameter gradients (training step)
+            torch.cat([grads[2].reshape(-1), grads[5], grads[6]], out=flat)
+            dist.all_reduce(flat)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(False)
+    sync_all()
+    sampler = ClockSampler(local)
+    sampler.start()
+    before = _lib.launch_count()
+    t_start, t_end = ev(), ev()
+    t_start.record()
+    for _ in range(args.steps):
+        step(True)
+    t_end.record()
+    sync_all()
+    launches = _lib.launch_count() - before
+    clocks = sampler.stop()
+    elapsed_ms = t_start.elapsed_time(t_end)
+    if world > 1:
+        tt = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(tt.item())
+    fwd_ms = sum(a.elapsed_time(b) for a, b in fwd_ev) / len(fwd_ev)
+    bwd_ms = sum(a.elapsed_time(b) for a, b in bwd_ev) / len(bwd_ev)
+
+    # ---- e2e: public autograd API, inputs start in pinned host memory every step
+    pin = {k: cast(k, host[k]).pin_memory() for k in ("x", "delta", "Bs", "Cs", "dy")}
+    h2d = sum(v.numel() * v.element_size() for v in pin.values())
+    params = {k: d[k].clone().requires_grad_(True) for k in ("A", "Ds", "delta_bias")}
+    out_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    copy_stream = torch.cuda.Stream(dev)
+    bufs = [{k: torch.empty_like(d[k] if k != "dy" else d["dy"]) for k in pin} for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]
+
+    def upload(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(free[i % 2])
+            for k, v in pin.items():
+                bufs[i % 2][k].copy_(v, non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    def e2e_steps(nsteps):
+        cur = torch.cuda.current_stream(dev)
+        for e in free:
+            e.record(cur)
+        upload(0)
+        for i in range(nsteps):
+            if i + 1 < nsteps:
+                upload(i + 1)                      # next step's inputs cross PCIe while this step computes
+            cur.wait_event(ready[i % 2])
+            b = bufs[i % 2]
+            x = b["x"].requires_grad_(True)
+            dl = b["delta"].requires_grad_(True)
+            Bs, Cs = b["Bs"].requires_grad_(True), b["Cs"].requires_grad_(True)
+            yy = ss2d_scan(x, dl, params["A"], Bs, Cs, params["Ds"], params["delta_bias"], True, True)
+            yy.backward(b["dy"])
+            res = yy.sum() + x.grad.sum()          # the step's scalar result, read back to the host
+            out_host.copy_(res.reshape(1), non_blocking=True)
+            for t_ in (x, dl, Bs, Cs):
+                t_.grad = None
+                t_.requires_grad_(False)
+            for p_ in params.values():
+                p_.grad = None
+            free[i % 2].record(cur)
+        cur.synchronize()
+
+    e2e_steps(min(3, args.warmup))
+    sync_all()
+    e_s, e_e = ev(), ev()
+    e_s.record()
+    e2e_steps(args.steps)
+    e_e.record()
+    sync_all()
+    e2e_ms = e_s.elapsed_time(e_e)
+    if world > 1:
+        tt = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt.item())
+
+    pairs_per_step = world * batch / 2
+    value = pairs_per_step * args.steps / (elapsed_ms / 1e3)
+    e2e_value = pairs_per_step * args.steps / (e2e_ms / 1e3)
+    fb, bb = alg_bytes(batch, w["D"], w["N"], L, s)
+    peak, peak_src = peaks()
+    roof = lambda nbytes, ms, name: {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                     "frac": nbytes / (ms * 1e-3) / 1e9 / peak, "traffic": traffic_from_profiles(name),
+                                     "kernel": name, "alg_bytes": nbytes, "avg_ms": ms, "peak_source": peak_src,
+                                     "frac_of_8TBs": nbytes / (ms * 1e-3) / 8e12}
+    line = {
+        "metric": "two_view_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": w["name"], "H": w["H"], "W": w["W"], "d_inner": w["D"], "d_state": w["N"], "K": w["K"],
+                   "images_per_gpu": batch, "pairs_per_step": pairs_per_step, "parallelism": f"dp{world}",
+                   "l2": "inputs per step (>0.9 GB fp32) exceed the 126 MB L2; no flush needed"},
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_ms / args.steps, "note": "pinned host inputs, double-buffered H2D on a copy stream"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roof(bb, bwd_ms, "ss2d_bwd_kernel"),
+        "roofline_fwd": roof(fb, fwd_ms, "ss2d_fwd_kernel"),
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+            sample = 8
+            v, secs = cpu_baseline(sample, reps=2)
+            line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
+                                    "sample": f"{sample} images (4 pairs), same SS2D core fwd+bwd, oracle/ C port + OpenMP, best of 2 ({secs:.2f} s)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step (2 images = 1 two-view pair)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

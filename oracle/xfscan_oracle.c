@@ -142,9 +142,13 @@ void XFO_NAME(xfo_selective_scan_fwd)(const real_t* u, const real_t* delta, cons
                                       real_t* out, real_t* last_state, int64_t Bsz, int64_t KD, int64_t K, int64_t N,
                                       int64_t L) {
     const int64_t Cdim = KD / K;
-    real_t* h = (real_t*)malloc(sizeof(real_t) * (size_t)N);
+    /* sequences are independent: one (b, d) row per OpenMP task (used by bench.py's CPU baseline; results do not
+     * depend on the thread count) */
+#pragma omp parallel for collapse(2) schedule(static)
     for (int64_t b = 0; b < Bsz; ++b)
         for (int64_t d = 0; d < KD; ++d) {
+            real_t hbuf[256];
+            real_t* h = (N <= 256) ? hbuf : (real_t*)malloc(sizeof(real_t) * (size_t)N);
             const int64_t g = d / Cdim;                                /* :53-54  B.view(..).repeat(1,1,Cdim,1,1) */
             const real_t* ur = u + (b * KD + d) * L;
             const real_t* dr = delta + (b * KD + d) * L;
@@ -167,8 +171,8 @@ void XFO_NAME(xfo_selective_scan_fwd)(const real_t* u, const real_t* delta, cons
             }
             if (last_state)
                 for (int64_t n = 0; n < N; ++n) last_state[(b * KD + d) * N + n] = h[n];
+            if (h != hbuf) free(h);
         }
-    free(h);
 }
 
 /* ---------------------------------------------------------------------------------------------
@@ -185,10 +189,13 @@ void XFO_NAME(xfo_selective_scan_bwd)(const real_t* u, const real_t* delta, cons
                                       real_t* dC, real_t* dD, real_t* dbias, int64_t Bsz, int64_t KD, int64_t K,
                                       int64_t N, int64_t L) {
     const int64_t Cdim = KD / K;
-    real_t* hs = (real_t*)malloc(sizeof(real_t) * (size_t)(N * (L + 1)));   /* hs[n][l+1] = h_l, hs[n][0] = 0 */
-    real_t* dts = (real_t*)malloc(sizeof(real_t) * (size_t)L);
-    real_t* dh = (real_t*)malloc(sizeof(real_t) * (size_t)N);
-    for (int64_t b = 0; b < Bsz; ++b)
+    /* parallel over batch images: dB/dC rows belong to one image; dA/dD/dbias are summed over images -> atomics
+     * (summation order over b then depends on scheduling: fine for a baseline timer, tests run single-threaded) */
+#pragma omp parallel for schedule(static)
+    for (int64_t b = 0; b < Bsz; ++b) {
+        real_t* hs = (real_t*)malloc(sizeof(real_t) * (size_t)(N * (L + 1)));   /* hs[n][l+1] = h_l, hs[n][0] = 0 */
+        real_t* dts = (real_t*)malloc(sizeof(real_t) * (size_t)L);
+        real_t* dh = (real_t*)malloc(sizeof(real_t) * (size_t)N);
         for (int64_t d = 0; d < KD; ++d) {
             const int64_t g = d / Cdim;
             const real_t* ur = u + (b * KD + d) * L;
@@ -211,6 +218,9 @@ void XFO_NAME(xfo_selective_scan_bwd)(const real_t* u, const real_t* delta, cons
                     hn[l + 1] = (real_t)exp((double)(dts[l] * A[d * N + n])) * hn[l] + (dts[l] * Bg[n * L + l]) * ur[l];
                 dh[n] = 0;
             }
+            real_t dA_acc[256];
+            real_t dD_acc = 0, dbias_acc = 0;
+            for (int64_t n = 0; n < N && n < 256; ++n) dA_acc[n] = 0;
             for (int64_t l = L - 1; l >= 0; --l) {
                 const real_t dy = dyr[l];
                 real_t du_l = D ? D[d] * dy : 0;
@@ -223,22 +233,35 @@ void XFO_NAME(xfo_selective_scan_bwd)(const real_t* u, const real_t* delta, cons
                     const real_t dhl = Cg[n * L + l] * dy + dh[n];
                     du_l += dhl * dts[l] * Bg[n * L + l];
                     ddt += dhl * (Bg[n * L + l] * ur[l] + a * abar * hn[l]);
-                    dA[d * N + n] += dhl * dts[l] * abar * hn[l];
+                    dA_acc[n] += dhl * dts[l] * abar * hn[l];
                     dBg[n * L + l] += dhl * dts[l] * ur[l];
                     dCg[n * L + l] += dy * hn[l + 1];
                     dh[n] = abar * dhl;
                 }
-                if (D) dD[d] += dy * ur[l];
+                if (D) dD_acc += dy * ur[l];
                 du[(b * KD + d) * L + l] = du_l;
                 if (delta_softplus) {
                     real_t raw = dr[l] + (delta_bias ? delta_bias[d] : 0);
                     if (raw <= (real_t)20) ddt = ddt * (real_t)(1.0 / (1.0 + exp(-(double)raw)));
                 }
                 ddelta[(b * KD + d) * L + l] = ddt;
-                if (delta_bias) dbias[d] += ddt;
+                if (delta_bias) dbias_acc += ddt;
+            }
+            for (int64_t n = 0; n < N; ++n) {
+#pragma omp atomic
+                dA[d * N + n] += dA_acc[n];
+            }
+            if (D) {
+#pragma omp atomic
+                dD[d] += dD_acc;
+            }
+            if (delta_bias) {
+#pragma omp atomic
+                dbias[d] += dbias_acc;
             }
         }
-    free(hs);
-    free(dts);
-    free(dh);
+        free(hs);
+        free(dts);
+        free(dh);
+    }
 }

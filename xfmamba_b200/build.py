@@ -19,7 +19,7 @@ CSRC = PKG / "csrc"
 SO = PKG / "libxfscan.so"
 OBJ = PKG / "build"
 SOURCES = ["routes.cu", "selective_scan.cu", "ss2d_fused.cu", "capi.cu"]
-HEADERS = [CSRC / "xfscan_common.cuh", PKG.parent / "include" / "xfscan.h"]
+HEADERS = [CSRC / "xfscan_common.cuh", CSRC / "ss2d_tiles.cuh", PKG.parent / "include" / "xfscan.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -7,76 +7,55 @@
 // read once, delta/B/C are streamed once, the merged y is written once: 6 elements per (b, d, l) + B/C.
 //
 // Work decomposition
-//   CTA  = one batch image x kCh (2) adjacent channels; 4 warps = the 4 routes, all running concurrently.
-//   The two channels of a CTA share the B/C values of a route (they live in registers once per chunk).
-//   Shared memory holds, per channel, the image row in row-major order (xN) and column-major order (xT) and the two
-//   accumulators yN (routes 0+2) and yT (routes 1+3), all indexed by POSITION with a 128-byte XOR swizzle so that
-//   "lane reads its 8 consecutive floats as two float4" is bank-conflict free.
+//   CTA  = one batch image x kCh adjacent channels; 4 warps = the 4 routes, all running concurrently.
+//   The channels of a CTA share the B/C values of a route (they live in registers once per chunk).
+//   Shared memory holds, per channel, the image in row-major order (xN) and column-major order (xT) and the two
+//   accumulators yN (routes 0+2) and yT (routes 1+3), all indexed by POSITION (ss2d_tiles.cuh).
 //   Routes 2/3 walk the same position chunks as routes 0/1 but from the far end (reverse warp scan), so a route and
 //   its flip never touch the same accumulator chunk in the same half of the walk: the first half stores, then one
 //   64-thread named barrier, then the second half read-modify-writes what the partner stored.  No atomics, and the
 //   sum (y0 + y2) + (y1 + y3) is evaluated in the reference's order (models/csm_triton.py:61-62).
 //   The S6 recurrence h_l = exp(dt_l A) h_{l-1} + dt_l B_l u_l is scanned per 256-position chunk with a warp-shuffle
 //   scan of affine maps (xfscan_common.cuh), state carried in registers (N == 1) or shared memory (N > 1).
-#include "xfscan_common.cuh"
+//   delta/B/C of the NEXT chunk are loaded (128-bit, register double buffer) before the current chunk is computed, and
+//   the element-wise arithmetic runs on packed fp32 pairs (FFMA2/FMUL2/FADD2).
+#include "ss2d_tiles.cuh"
 
 namespace xfs {
 
 constexpr int kChFwd = 2;                    // channels per CTA, forward
-constexpr int kChBwd = 1;                    // channels per CTA, backward (register budget: see DESIGN.md)
+constexpr int kChBwd = 1;                    // channels per CTA, backward (register + shared-memory budget)
 constexpr int kFusedMaxState = 64;           // states carried in smem for N > 1
-
-__host__ __device__ inline int64_t buf_len(int64_t L) { return ((L + kChunk - 1) / kChunk) * kChunk; }
-
-// position -> float offset inside a swizzled buffer (16-byte granules XORed with bits 3..5 of the granule index)
-__device__ __forceinline__ int swz_f4(int f) { return f ^ ((f >> 3) & 7); }
-__device__ __forceinline__ int swz_pos(int p) { return (swz_f4(p >> 2) << 2) | (p & 3); }
-
-__device__ __forceinline__ void lds8(const float* buf, int f4s, float (&v)[8]) {
-    const float4 a = *reinterpret_cast<const float4*>(buf + (f4s << 2));
-    const float4 b = *reinterpret_cast<const float4*>(buf + ((f4s ^ 1) << 2));
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-__device__ __forceinline__ void sts8(float* buf, int f4s, const float (&v)[8]) {
-    *reinterpret_cast<float4*>(buf + (f4s << 2)) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(buf + ((f4s ^ 1) << 2)) = make_float4(v[4], v[5], v[6], v[7]);
-}
 
 __device__ __forceinline__ void pair_barrier(int pair) {   // the 2 warps of a route pair (routes k and k+2)
     asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
 }
 
-// Stage one (b, d) image row into the row-major and column-major swizzled buffers; zero the tails.
-template <typename T>
-__device__ __forceinline__ void stage_image(const T* __restrict__ img, float* __restrict__ bN, float* __restrict__ bT,
-                                            int H, int W, int L, int Lb, bool valid, int tid, int nthreads) {
-    for (int p = tid; p < Lb; p += nthreads) {
-        float v = 0.0f;
-        if (valid && p < L) v = Elem<T>::to_f(img[p]);
-        bN[swz_pos(p)] = v;
-        if (p < L) {
-            const int h = p / W, w = p - h * W;
-            bT[swz_pos(w * H + h)] = v;
-        } else {
-            bT[swz_pos(p)] = 0.0f;       // positions L..Lb-1 are the tail of BOTH layouts
-        }
-    }
+__device__ __forceinline__ void pack8(const float (&v)[8], f2 (&o)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = make_float2(v[2 * j], v[2 * j + 1]);
 }
 
 // =========================================================================================================
 // forward
 // =========================================================================================================
+template <typename T, int kN, int kCh>
+struct FwdChunk {            // raw inputs of one chunk of one route (position order)
+    float dt[kCh][8];
+    float B[8], C[8];       // kN == 1 only
+};
+
 template <typename T, typename TO, int kN, int kCh>   // kN == 1: single state in registers; kN == 0: runtime N (<= kFusedMaxState)
 __global__ void __launch_bounds__(128)
 ss2d_fwd_kernel(const xfs_ss2d_fwd_args p) {
     extern __shared__ __align__(16) float smem[];
     const int H = (int)p.H, W = (int)p.W, L = H * W;
     const int Lb = (int)buf_len(L), nch = Lb / kChunk;
-    const int64_t D = p.D;
+    const int D = (int)p.D;
     const int N = (kN == 1) ? 1 : (int)p.N;
-    const int64_t pairs = (D + kCh - 1) / kCh;
-    const int64_t b = blockIdx.x / pairs;
-    const int64_t d0 = (blockIdx.x % pairs) * kCh;
+    const int groups = (D + kCh - 1) / kCh;
+    const int b = blockIdx.x / groups;
+    const int d0 = (blockIdx.x - b * groups) * kCh;
     const int tid = threadIdx.x, lane = tid & 31, k = tid >> 5;     // warp k runs route k
     const bool rev = k >= 2, transposed = k & 1;
     bool valid[kCh];
@@ -92,7 +71,7 @@ ss2d_fwd_kernel(const xfs_ss2d_fwd_args p) {
     const T* __restrict__ x = reinterpret_cast<const T*>(p.x);
 #pragma unroll
     for (int ch = 0; ch < kCh; ++ch)
-        stage_image<T>(x + (b * D + (valid[ch] ? d0 + ch : d0)) * L, xN + ch * Lb, xT + ch * Lb, H, W, L, Lb, valid[ch], tid, 128);
+        stage_image<T>(x + ((int64_t)b * D + (valid[ch] ? d0 + ch : d0)) * L, xN + ch * Lb, xT + ch * Lb, H, W, L, Lb, valid[ch], tid, 128);
     if (kN == 0)
         for (int i = tid; i < 4 * kCh * kFusedMaxState; i += 128) s_h[i] = 0.0f;
     __syncthreads();
@@ -100,18 +79,20 @@ ss2d_fwd_kernel(const xfs_ss2d_fwd_args p) {
     const float* xb = transposed ? xT : xN;
     float* yb = transposed ? yT : yN;
     const T* __restrict__ delta = reinterpret_cast<const T*>(p.delta);
-    const T* __restrict__ Bk = reinterpret_cast<const T*>(p.Bs) + (b * 4 + k) * (int64_t)N * L;
-    const T* __restrict__ Ck = reinterpret_cast<const T*>(p.Cs) + (b * 4 + k) * (int64_t)N * L;
+    const T* __restrict__ Bk = reinterpret_cast<const T*>(p.Bs) + ((int64_t)b * 4 + k) * N * L;
+    const T* __restrict__ Ck = reinterpret_cast<const T*>(p.Cs) + ((int64_t)b * 4 + k) * N * L;
     const bool vin = row_vec_ok(delta, L) && row_vec_ok(reinterpret_cast<const T*>(p.Bs), L) &&
                      row_vec_ok(reinterpret_cast<const T*>(p.Cs), L);
 
     const T* dt_row[kCh];
+    float* st_row[kCh];
     float bias[kCh], Dd[kCh], A2_1[kCh], carry1[kCh];
-    int64_t kd[kCh];
+    int kd[kCh];
 #pragma unroll
     for (int ch = 0; ch < kCh; ++ch) {
         kd[ch] = k * D + (valid[ch] ? d0 + ch : d0);
-        dt_row[ch] = delta + (b * 4 * D + kd[ch]) * L;
+        dt_row[ch] = delta + ((int64_t)b * 4 * D + kd[ch]) * L;
+        st_row[ch] = (p.states && valid[ch]) ? p.states + ((int64_t)b * 4 * D + kd[ch]) * nch * N : nullptr;
         bias[ch] = p.delta_bias ? p.delta_bias[kd[ch]] : 0.0f;
         Dd[ch] = p.Ds ? p.Ds[kd[ch]] : 0.0f;
         A2_1[ch] = (kN == 1) ? p.A[kd[ch]] * kLog2e : 0.0f;
@@ -120,51 +101,83 @@ ss2d_fwd_kernel(const xfs_ss2d_fwd_args p) {
 
     const int m = (nch + 1) / 2;        // chunks [0, m) are first touched by the forward route, [m, nch) by its flip
     bool synced = false;
-    for (int step = 0; step < nch; ++step) {
+
+    auto load_chunk = [&](int step, FwdChunk<T, kN, kCh>& c) {
         const int j = rev ? (nch - 1 - step) : step;
         const int p0 = j * kChunk + lane * kItems;
-        const int64_t l0 = rev ? (int64_t)L - 8 - p0 : (int64_t)p0;     // scan index of the lowest-address element
-        const int f4s = swz_f4(p0 >> 2);
-
-        float dt[kCh][8], u[kCh][8], y[kCh][8];
+        const int l0 = rev ? L - 8 - p0 : p0;            // scan index of the lowest-address element
 #pragma unroll
         for (int ch = 0; ch < kCh; ++ch) {
-            load8(dt_row[ch], l0, L, vin, dt[ch]);
-            if (rev) reverse8(dt[ch]);
-            lds8(xb + ch * Lb, f4s, u[ch]);
+            load8(dt_row[ch], l0, L, vin, c.dt[ch]);
+            if (rev) reverse8(c.dt[ch]);
+        }
+        if (kN == 1) {
+            load8(Bk, l0, L, vin, c.B);
+            load8(Ck, l0, L, vin, c.C);
+            if (rev) { reverse8(c.B); reverse8(c.C); }
+        }
+    };
+
+    auto compute_chunk = [&](int step, FwdChunk<T, kN, kCh>& c) {
+        const int j = rev ? (nch - 1 - step) : step;
+        const int p0 = j * kChunk + lane * kItems;
+        const int l0 = rev ? L - 8 - p0 : p0;
+        const int f4s = swz_f4(p0 >> 2);
+        const bool tail = p0 + 8 > L;
+
+        f2 dt2[kCh][4], u2[kCh][4], y2[kCh][4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float xx = dt[ch][i] + bias[ch], e;
-                float sp = p.delta_softplus ? softplus_fwd(xx, e) : xx;
-                dt[ch][i] = (p0 + i < L) ? sp : 0.0f;
-                y[ch][i] = Dd[ch] * u[ch][i];
+        for (int ch = 0; ch < kCh; ++ch) {
+            float u[8];
+            lds8(xb + ch * Lb, f4s, u);
+            pack8(u, u2[ch]);
+            pack8(c.dt[ch], dt2[ch]);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const f2 xx = add2(dt2[ch][jj], splat2(bias[ch]));
+                f2 e;
+                dt2[ch][jj] = p.delta_softplus ? softplus2(xx, e) : xx;
+                y2[ch][jj] = mul2(splat2(Dd[ch]), u2[ch][jj]);
+            }
+            if (tail) {                                   // positions >= L: identity map (dt = 0)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    if (p0 + 2 * jj >= L) dt2[ch][jj].x = 0.0f;
+                    if (p0 + 2 * jj + 1 >= L) dt2[ch][jj].y = 0.0f;
+                }
             }
         }
         for (int n = 0; n < N; ++n) {
-            float Bv[8], Cv[8];
-            load8(Bk + (int64_t)n * L, l0, L, vin, Bv);
-            load8(Ck + (int64_t)n * L, l0, L, vin, Cv);
-            if (rev) { reverse8(Bv); reverse8(Cv); }
+            f2 B2[4], C2[4];
+            if (kN == 1) { pack8(c.B, B2); pack8(c.C, C2); }
+            else {
+                float Bv[8], Cv[8];
+                load8(Bk + n * L, l0, L, vin, Bv);
+                load8(Ck + n * L, l0, L, vin, Cv);
+                if (rev) { reverse8(Bv); reverse8(Cv); }
+                pack8(Bv, B2); pack8(Cv, C2);
+            }
 #pragma unroll
             for (int ch = 0; ch < kCh; ++ch) {
                 const float A2 = (kN == 1) ? A2_1[ch] : p.A[kd[ch] * N + n] * kLog2e;
-                float S[8], P[8];
+                f2 a2[4], bu2[4], S2[4], P2[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    a2[jj] = ex2_2(mul2(dt2[ch][jj], splat2(A2)));
+                    bu2[jj] = mul2(mul2(dt2[ch][jj], B2[jj]), u2[ch][jj]);
+                }
                 float Pr = 1.0f, Sr = 0.0f;
                 if (!rev) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float a = ex2(dt[ch][i] * A2);
-                        Sr = fmaf(a, Sr, (dt[ch][i] * Bv[i]) * u[ch][i]);
-                        Pr *= a;
-                        S[i] = Sr; P[i] = Pr;
+                    for (int jj = 0; jj < 4; ++jj) {
+                        Sr = fmaf(a2[jj].x, Sr, bu2[jj].x); Pr *= a2[jj].x; S2[jj].x = Sr; P2[jj].x = Pr;
+                        Sr = fmaf(a2[jj].y, Sr, bu2[jj].y); Pr *= a2[jj].y; S2[jj].y = Sr; P2[jj].y = Pr;
                     }
                 } else {
 #pragma unroll
-                    for (int i = 7; i >= 0; --i) {
-                        const float a = ex2(dt[ch][i] * A2);
-                        Sr = fmaf(a, Sr, (dt[ch][i] * Bv[i]) * u[ch][i]);
-                        Pr *= a;
-                        S[i] = Sr; P[i] = Pr;
+                    for (int jj = 3; jj >= 0; --jj) {
+                        Sr = fmaf(a2[jj].y, Sr, bu2[jj].y); Pr *= a2[jj].y; S2[jj].y = Sr; P2[jj].y = Pr;
+                        Sr = fmaf(a2[jj].x, Sr, bu2[jj].x); Pr *= a2[jj].x; S2[jj].x = Sr; P2[jj].x = Pr;
                     }
                 }
                 float* hs = s_h + (k * kCh + ch) * kFusedMaxState + n;
@@ -172,12 +185,12 @@ ss2d_fwd_kernel(const xfs_ss2d_fwd_args p) {
                 float h_out;
                 const float h_in = rev ? warp_prefix<true>(Pr, Sr, carry, lane, h_out)
                                        : warp_prefix<false>(Pr, Sr, carry, lane, h_out);
+                const f2 hin2 = splat2(h_in);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) y[ch][i] = fmaf(Cv[i], fmaf(P[i], h_in, S[i]), y[ch][i]);
+                for (int jj = 0; jj < 4; ++jj) y2[ch][jj] = fma2(C2[jj], fma2(P2[jj], hin2, S2[jj]), y2[ch][jj]);
                 if (kN == 1) carry1[ch] = h_out;
                 else { __syncwarp(); if (lane == 0) *hs = h_out; }
-                if (p.states && lane == 0 && valid[ch])
-                    p.states[((b * 4 * D + kd[ch]) * nch + j) * N + n] = h_out;
+                if (st_row[ch] && lane == 0) st_row[ch][j * N + n] = h_out;
             }
         }
         // accumulate into the pair's buffer
@@ -185,13 +198,30 @@ ss2d_fwd_kernel(const xfs_ss2d_fwd_args p) {
         if (!first_touch && !synced) { pair_barrier(k & 1); synced = true; }
 #pragma unroll
         for (int ch = 0; ch < kCh; ++ch) {
+            float* yc = yb + ch * Lb;
+            float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
             if (!first_touch) {
-                float o[8];
-                lds8(yb + ch * Lb, f4s, o);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) y[ch][i] += o[i];
+                o0 = *reinterpret_cast<const float4*>(yc + (f4s << 2));
+                o1 = *reinterpret_cast<const float4*>(yc + ((f4s ^ 1) << 2));
             }
-            sts8(yb + ch * Lb, f4s, y[ch]);
+            const f2 r0 = add2(y2[ch][0], make_float2(o0.x, o0.y)), r1 = add2(y2[ch][1], make_float2(o0.z, o0.w));
+            const f2 r2 = add2(y2[ch][2], make_float2(o1.x, o1.y)), r3 = add2(y2[ch][3], make_float2(o1.z, o1.w));
+            *reinterpret_cast<float4*>(yc + (f4s << 2)) = make_float4(r0.x, r0.y, r1.x, r1.y);
+            *reinterpret_cast<float4*>(yc + ((f4s ^ 1) << 2)) = make_float4(r2.x, r2.y, r3.x, r3.y);
+        }
+    };
+
+    {
+        FwdChunk<T, kN, kCh> ca, cb;
+        load_chunk(0, ca);
+#pragma unroll 1
+        for (int step = 0; step < nch; step += 2) {
+            if (step + 1 < nch) load_chunk(step + 1, cb);
+            compute_chunk(step, ca);
+            if (step + 1 < nch) {
+                if (step + 2 < nch) load_chunk(step + 2, ca);
+                compute_chunk(step + 1, cb);
+            }
         }
     }
     if (!synced) pair_barrier(k & 1);
@@ -200,14 +230,8 @@ ss2d_fwd_kernel(const xfs_ss2d_fwd_args p) {
     // merged output, spatial order: y[p] = yN[p] + yT[w*H + h]
     TO* __restrict__ out = reinterpret_cast<TO*>(p.y);
 #pragma unroll
-    for (int ch = 0; ch < kCh; ++ch) {
-        if (!valid[ch]) continue;
-        TO* __restrict__ orow = out + (b * D + d0 + ch) * L;
-        for (int pp = tid; pp < L; pp += 128) {
-            const int h = pp / W, w = pp - h * W;
-            orow[pp] = Elem<TO>::from_f(yN[ch * Lb + swz_pos(pp)] + yT[ch * Lb + swz_pos(w * H + h)]);
-        }
-    }
+    for (int ch = 0; ch < kCh; ++ch)
+        if (valid[ch]) merge_out<TO>(out + ((int64_t)b * D + d0 + ch) * L, yN + ch * Lb, yT + ch * Lb, H, W, tid, 128);
 }
 
 // =========================================================================================================
@@ -218,17 +242,24 @@ ss2d_fwd_kernel(const xfs_ss2d_fwd_args p) {
 //     closed forms listed in selective_scan.cu.  dBs/dCs: the CTA's channels are summed in registers, then one
 //     fp32 atomic per (route, n, l); dA/dDs/dbias: warp-reduced, one atomic per (route, channel).
 // =========================================================================================================
+template <typename T, int kN, int kCh>
+struct BwdChunk {
+    float dt[kCh][8];
+    float B[8], C[8];
+    float hstart[kCh];      // kN == 1: checkpointed state entering the chunk
+};
+
 template <typename T, typename TDO, int kN, int kCh>
 __global__ void __launch_bounds__(128)
 ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
     extern __shared__ __align__(16) float smem[];
     const int H = (int)p.H, W = (int)p.W, L = H * W;
     const int Lb = (int)buf_len(L), nch = Lb / kChunk;
-    const int64_t D = p.D;
+    const int D = (int)p.D;
     const int N = (kN == 1) ? 1 : (int)p.N;
-    const int64_t pairs = (D + kCh - 1) / kCh;
-    const int64_t b = blockIdx.x / pairs;
-    const int64_t d0 = (blockIdx.x % pairs) * kCh;
+    const int groups = (D + kCh - 1) / kCh;
+    const int b = blockIdx.x / groups;
+    const int d0 = (blockIdx.x - b * groups) * kCh;
     const int tid = threadIdx.x, lane = tid & 31, k = tid >> 5;
     const bool rev = k >= 2, transposed = k & 1;     // `rev` is the FORWARD walk direction of this route
     bool valid[kCh];
@@ -248,7 +279,7 @@ ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
     const TDO* __restrict__ dyp = reinterpret_cast<const TDO*>(p.dy);
 #pragma unroll
     for (int ch = 0; ch < kCh; ++ch) {
-        const int64_t row = (b * D + (valid[ch] ? d0 + ch : d0)) * L;
+        const int64_t row = ((int64_t)b * D + (valid[ch] ? d0 + ch : d0)) * L;
         stage_image<T>(x + row, xN + ch * Lb, xT + ch * Lb, H, W, L, Lb, valid[ch], tid, 128);
         stage_image<TDO>(dyp + row, gN + ch * Lb, gT + ch * Lb, H, W, L, Lb, valid[ch], tid, 128);
     }
@@ -261,23 +292,26 @@ ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
     float* db = transposed ? dT : dN;
     const T* __restrict__ delta = reinterpret_cast<const T*>(p.delta);
     T* __restrict__ ddelta = reinterpret_cast<T*>(p.ddelta);
-    const T* __restrict__ Bk = reinterpret_cast<const T*>(p.Bs) + (b * 4 + k) * (int64_t)N * L;
-    const T* __restrict__ Ck = reinterpret_cast<const T*>(p.Cs) + (b * 4 + k) * (int64_t)N * L;
-    float* __restrict__ dBk = p.dBs + (b * 4 + k) * (int64_t)N * L;
-    float* __restrict__ dCk = p.dCs + (b * 4 + k) * (int64_t)N * L;
+    const T* __restrict__ Bk = reinterpret_cast<const T*>(p.Bs) + ((int64_t)b * 4 + k) * N * L;
+    const T* __restrict__ Ck = reinterpret_cast<const T*>(p.Cs) + ((int64_t)b * 4 + k) * N * L;
+    float* __restrict__ dBk = p.dBs + ((int64_t)b * 4 + k) * N * L;
+    float* __restrict__ dCk = p.dCs + ((int64_t)b * 4 + k) * N * L;
     const bool vin = row_vec_ok(delta, L) && row_vec_ok(reinterpret_cast<const T*>(p.Bs), L) &&
                      row_vec_ok(reinterpret_cast<const T*>(p.Cs), L);
     const bool vout = row_vec_ok(ddelta, L);
+    const bool vacc = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.dBs) & 15) == 0) && ((reinterpret_cast<uintptr_t>(p.dCs) & 15) == 0);
 
     const T* dt_row[kCh];
     T* ddt_row[kCh];
+    const float* st_row[kCh];
     float bias[kCh], Dd[kCh], A_1[kCh], qcarry1[kCh], dA1[kCh], dD_acc[kCh], dbias_acc[kCh];
-    int64_t kd[kCh];
+    int kd[kCh];
 #pragma unroll
     for (int ch = 0; ch < kCh; ++ch) {
         kd[ch] = k * D + (valid[ch] ? d0 + ch : d0);
-        dt_row[ch] = delta + (b * 4 * D + kd[ch]) * L;
-        ddt_row[ch] = ddelta + (b * 4 * D + kd[ch]) * L;
+        dt_row[ch] = delta + ((int64_t)b * 4 * D + kd[ch]) * L;
+        ddt_row[ch] = ddelta + ((int64_t)b * 4 * D + kd[ch]) * L;
+        st_row[ch] = p.states + ((int64_t)b * 4 * D + kd[ch]) * nch * N;
         bias[ch] = p.delta_bias ? p.delta_bias[kd[ch]] : 0.0f;
         Dd[ch] = p.Ds ? p.Ds[kd[ch]] : 0.0f;
         A_1[ch] = (kN == 1) ? p.A[kd[ch]] : 0.0f;
@@ -286,28 +320,53 @@ ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
 
     // The backward of route k walks its chunks in the reverse of the forward walk: routes 0/1 go nch-1 -> 0 with a
     // reverse (lanes 31->0) adjoint scan, routes 2/3 go 0 -> nch-1 with a lanes 0->31 adjoint scan.
-    const int m = nch / 2;             // bwd-forward-walking routes (2/3) first touch [0, m); routes 0/1 first touch [m, nch)
+    const int m = nch / 2;             // routes 2/3 first touch [0, m); routes 0/1 first touch [m, nch)
     bool synced = false;
-    for (int step = 0; step < nch; ++step) {
+
+    auto load_chunk = [&](int step, BwdChunk<T, kN, kCh>& c) {
         const int j = rev ? step : (nch - 1 - step);
         const int p0 = j * kChunk + lane * kItems;
-        const int64_t l0 = rev ? (int64_t)L - 8 - p0 : (int64_t)p0;
+        const int l0 = rev ? L - 8 - p0 : p0;
+        const int jprev = rev ? j + 1 : j - 1;           // chunk the forward walked just before this one
+#pragma unroll
+        for (int ch = 0; ch < kCh; ++ch) {
+            load8(dt_row[ch], l0, L, vin, c.dt[ch]);
+            if (rev) reverse8(c.dt[ch]);
+            if (kN == 1) c.hstart[ch] = (jprev >= 0 && jprev < nch) ? st_row[ch][jprev] : 0.0f;
+        }
+        if (kN == 1) {
+            load8(Bk, l0, L, vin, c.B);
+            load8(Ck, l0, L, vin, c.C);
+            if (rev) { reverse8(c.B); reverse8(c.C); }
+        }
+    };
+
+    auto compute_chunk = [&](int step, BwdChunk<T, kN, kCh>& c) {
+        const int j = rev ? step : (nch - 1 - step);
+        const int p0 = j * kChunk + lane * kItems;
+        const int l0 = rev ? L - 8 - p0 : p0;
+        const int jprev = rev ? j + 1 : j - 1;
         const int f4s = swz_f4(p0 >> 2);
+        const bool tail = p0 + 8 > L;
 
         float dt[kCh][8], u[kCh][8], dy[kCh][8], sig[kCh][8], du[kCh][8], ddt[kCh][8];
 #pragma unroll
         for (int ch = 0; ch < kCh; ++ch) {
-            load8(dt_row[ch], l0, L, vin, dt[ch]);
-            if (rev) reverse8(dt[ch]);
             lds8(xb + ch * Lb, f4s, u[ch]);
             lds8(gb + ch * Lb, f4s, dy[ch]);
 #pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const f2 xx = add2(make_float2(c.dt[ch][2 * jj], c.dt[ch][2 * jj + 1]), splat2(bias[ch]));
+                f2 e = splat2(0.0f);
+                const f2 sp = p.delta_softplus ? softplus2(xx, e) : xx;
+                dt[ch][2 * jj] = sp.x; dt[ch][2 * jj + 1] = sp.y;
+                // sigmoid(x) = e / (1 + e); x > 20 -> 1 (softplus is the identity there)
+                sig[ch][2 * jj] = p.delta_softplus ? ((xx.x > 20.0f) ? 1.0f : e.x * rcp(1.0f + e.x)) : 1.0f;
+                sig[ch][2 * jj + 1] = p.delta_softplus ? ((xx.y > 20.0f) ? 1.0f : e.y * rcp(1.0f + e.y)) : 1.0f;
+            }
+#pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float xx = dt[ch][i] + bias[ch];
-                float e = 0.0f;
-                const float sp = p.delta_softplus ? softplus_fwd(xx, e) : xx;
-                sig[ch][i] = p.delta_softplus ? ((xx > 20.0f) ? 1.0f : e * rcp(1.0f + e)) : 1.0f;
-                dt[ch][i] = (p0 + i < L) ? sp : 0.0f;
+                if (tail && p0 + i >= L) dt[ch][i] = 0.0f;
                 du[ch][i] = Dd[ch] * dy[ch][i];
                 ddt[ch][i] = 0.0f;
                 dD_acc[ch] = fmaf(dy[ch][i], u[ch][i], dD_acc[ch]);
@@ -315,9 +374,14 @@ ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
         }
         for (int n = 0; n < N; ++n) {
             float Bv[8], Cv[8], dBv[8], dCv[8];
-            load8(Bk + (int64_t)n * L, l0, L, vin, Bv);
-            load8(Ck + (int64_t)n * L, l0, L, vin, Cv);
-            if (rev) { reverse8(Bv); reverse8(Cv); }
+            if (kN == 1) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { Bv[i] = c.B[i]; Cv[i] = c.C[i]; }
+            } else {
+                load8(Bk + n * L, l0, L, vin, Bv);
+                load8(Ck + n * L, l0, L, vin, Cv);
+                if (rev) { reverse8(Bv); reverse8(Cv); }
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) { dBv[i] = 0.0f; dCv[i] = 0.0f; }
 #pragma unroll
@@ -326,39 +390,31 @@ ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
                 const float A2 = An * kLog2e;
                 float a[8], bu[8], S[8], P[8], Sq[8], Pq[8];
                 float Pr = 1.0f, Sr = 0.0f;
-                // state entering this chunk in the forward walk = checkpoint of the chunk walked just before it
-                const int jprev = rev ? j + 1 : j - 1;
-                const float h_start = (jprev >= 0 && jprev < nch) ? p.states[((b * 4 * D + kd[ch]) * nch + jprev) * N + n] : 0.0f;
+                const float h_start = (kN == 1) ? c.hstart[ch]
+                                                : ((jprev >= 0 && jprev < nch) ? st_row[ch][jprev * N + n] : 0.0f);
                 float unused, h_in, q_in, q_out;
                 float* qs = s_q + (k * kCh + ch) * kFusedMaxState + n;
                 const float qc = (kN == 1) ? qcarry1[ch] : *qs;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    a[i] = ex2(dt[ch][i] * A2);
+                    bu[i] = (dt[ch][i] * Bv[i]) * u[ch][i];
+                }
                 if (!rev) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        a[i] = ex2(dt[ch][i] * A2);
-                        bu[i] = (dt[ch][i] * Bv[i]) * u[ch][i];
-                        Sr = fmaf(a[i], Sr, bu[i]); Pr *= a[i]; S[i] = Sr; P[i] = Pr;
-                    }
+                    for (int i = 0; i < 8; ++i) { Sr = fmaf(a[i], Sr, bu[i]); Pr *= a[i]; S[i] = Sr; P[i] = Pr; }
                     h_in = warp_prefix<false>(Pr, Sr, h_start, lane, unused);
                     Pr = 1.0f; Sr = 0.0f;
 #pragma unroll
-                    for (int i = 7; i >= 0; --i) {
-                        Sr = a[i] * fmaf(Cv[i], dy[ch][i], Sr); Pr *= a[i]; Sq[i] = Sr; Pq[i] = Pr;
-                    }
+                    for (int i = 7; i >= 0; --i) { Sr = a[i] * fmaf(Cv[i], dy[ch][i], Sr); Pr *= a[i]; Sq[i] = Sr; Pq[i] = Pr; }
                     q_in = warp_prefix<true>(Pr, Sr, qc, lane, q_out);
                 } else {
 #pragma unroll
-                    for (int i = 7; i >= 0; --i) {
-                        a[i] = ex2(dt[ch][i] * A2);
-                        bu[i] = (dt[ch][i] * Bv[i]) * u[ch][i];
-                        Sr = fmaf(a[i], Sr, bu[i]); Pr *= a[i]; S[i] = Sr; P[i] = Pr;
-                    }
+                    for (int i = 7; i >= 0; --i) { Sr = fmaf(a[i], Sr, bu[i]); Pr *= a[i]; S[i] = Sr; P[i] = Pr; }
                     h_in = warp_prefix<true>(Pr, Sr, h_start, lane, unused);
                     Pr = 1.0f; Sr = 0.0f;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        Sr = a[i] * fmaf(Cv[i], dy[ch][i], Sr); Pr *= a[i]; Sq[i] = Sr; Pq[i] = Pr;
-                    }
+                    for (int i = 0; i < 8; ++i) { Sr = a[i] * fmaf(Cv[i], dy[ch][i], Sr); Pr *= a[i]; Sq[i] = Sr; Pq[i] = Pr; }
                     q_in = warp_prefix<false>(Pr, Sr, qc, lane, q_out);
                 }
                 float dA_part = 0.0f;
@@ -389,12 +445,21 @@ ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
             }
             // dB / dC of this route at scan positions l0..l0+7 (ascending address order)
             if (rev) { reverse8(dBv); reverse8(dCv); }
+            float* dBrow = dBk + n * L;
+            float* dCrow = dCk + n * L;
+            if (vacc && l0 >= 0 && l0 + 8 <= L) {
+                red_add_v4(dBrow + l0, dBv[0], dBv[1], dBv[2], dBv[3]);
+                red_add_v4(dBrow + l0 + 4, dBv[4], dBv[5], dBv[6], dBv[7]);
+                red_add_v4(dCrow + l0, dCv[0], dCv[1], dCv[2], dCv[3]);
+                red_add_v4(dCrow + l0 + 4, dCv[4], dCv[5], dCv[6], dCv[7]);
+            } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int64_t l = l0 + i;
-                if (l >= 0 && l < L) {
-                    atomicAdd(dBk + (int64_t)n * L + l, dBv[i]);
-                    atomicAdd(dCk + (int64_t)n * L + l, dCv[i]);
+                for (int i = 0; i < 8; ++i) {
+                    const int l = l0 + i;
+                    if (l >= 0 && l < L) {
+                        atomicAdd(dBrow + l, dBv[i]);
+                        atomicAdd(dCrow + l, dCv[i]);
+                    }
                 }
             }
         }
@@ -406,11 +471,11 @@ ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 ddt[ch][i] *= sig[ch][i];
-                if (p0 + i < L) dbias_acc[ch] += ddt[ch][i];
+                dbias_acc[ch] += ddt[ch][i];            // dt = 0 beyond L makes these terms exactly 0
             }
             if (valid[ch]) {
                 if (rev) reverse8(ddt[ch]);
-                store8(ddt_row[ch], l0, L, vout, ddt[ch]);
+                store8(ddt_row[ch], (int64_t)l0, (int64_t)L, vout, ddt[ch]);
             }
             if (!first_touch) {
                 float o[8];
@@ -419,6 +484,20 @@ ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
                 for (int i = 0; i < 8; ++i) du[ch][i] += o[i];
             }
             sts8(db + ch * Lb, f4s, du[ch]);
+        }
+    };
+
+    {
+        BwdChunk<T, kN, kCh> ca, cb;
+        load_chunk(0, ca);
+#pragma unroll 1
+        for (int step = 0; step < nch; step += 2) {
+            if (step + 1 < nch) load_chunk(step + 1, cb);
+            compute_chunk(step, ca);
+            if (step + 1 < nch) {
+                if (step + 2 < nch) load_chunk(step + 2, ca);
+                compute_chunk(step + 1, cb);
+            }
         }
     }
     if (!synced) pair_barrier(k & 1);
@@ -445,14 +524,8 @@ ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
     // dx[p] = dN[p] + dT[w*H + h]   (CrossScanF.backward = cross-merge of du, models/csm_triton.py:208-225)
     T* __restrict__ dx = reinterpret_cast<T*>(p.dx);
 #pragma unroll
-    for (int ch = 0; ch < kCh; ++ch) {
-        if (!valid[ch]) continue;
-        T* __restrict__ orow = dx + (b * D + d0 + ch) * L;
-        for (int pp = tid; pp < L; pp += 128) {
-            const int h = pp / W, w = pp - h * W;
-            orow[pp] = Elem<T>::from_f(dN[ch * Lb + swz_pos(pp)] + dT[ch * Lb + swz_pos(w * H + h)]);
-        }
-    }
+    for (int ch = 0; ch < kCh; ++ch)
+        if (valid[ch]) merge_out<T>(dx + ((int64_t)b * D + d0 + ch) * L, dN + ch * Lb, dT + ch * Lb, H, W, tid, 128);
 }
 
 // =========================================================================================================

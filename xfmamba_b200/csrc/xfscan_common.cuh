@@ -164,6 +164,39 @@ __device__ __forceinline__ float warp_prefix(float P, float S, float carry, int 
     return first ? carry : prev;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// packed fp32 (sm_100 FFMA2 / FMUL2 / FADD2: two fp32 lanes per issue slot on a 64-bit register pair)
+// ---------------------------------------------------------------------------------------------------------
+using f2 = float2;
+__device__ __forceinline__ f2 splat2(float v) { return make_float2(v, v); }
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 ex2_2(f2 a) { return make_float2(ex2(a.x), ex2(a.y)); }
+
+// softplus on a pair (same semantics as softplus_fwd); e_out = exp(x)
+__device__ __forceinline__ f2 softplus2(f2 x, f2& e_out) {
+    const f2 e = ex2_2(mul2(x, splat2(kLog2e)));
+    e_out = e;
+    const f2 w = add2(e, splat2(1.0f));
+    const f2 big = mul2(make_float2(lg2(w.x), lg2(w.y)), splat2(kLn2));
+    f2 ser = fma2(e, splat2(-0.25f), splat2(0.33333334f));
+    ser = fma2(ser, e, splat2(-0.5f));
+    ser = fma2(ser, e, splat2(1.0f));
+    ser = mul2(ser, e);
+    f2 r;
+    r.x = (e.x < 0.015625f) ? ser.x : big.x;
+    r.y = (e.y < 0.015625f) ? ser.y : big.y;
+    r.x = (x.x > 20.0f) ? x.x : r.x;
+    r.y = (x.y > 20.0f) ? x.y : r.y;
+    return r;
+}
+
+// 16-byte vector reduction into global memory (sm_90+): one L2 atomic op for 4 consecutive floats
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);

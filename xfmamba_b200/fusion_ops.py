@@ -19,7 +19,7 @@ from .csm import cross_merge_raw, cross_scan_raw
 from .csms6s import _check_scan_args, selective_scan_bwd_raw, selective_scan_fwd_raw
 
 __all__ = ["SwappingScan_multiview", "SwappingMerge_multiview", "swapping_scan", "swapping_merge", "ss2d_scan",
-           "SS2DScanFn", "ss2d_fused_supported"]
+           "SS2DScanFn", "ss2d_fused_supported", "ss2d_fwd_raw", "ss2d_bwd_raw"]
 
 
 def _swap_call(fn_name, a, b, outs, B, C, L, dev):
@@ -120,6 +120,53 @@ def ss2d_fused_supported(D: int, N: int, H: int, W: int, dtype: torch.dtype, bac
     return bool(_lib.lib().xfs_ss2d_supported(D, N, H, W, _lib._DTYPES[dtype], int(backward)))
 
 
+def ss2d_fwd_raw(x, delta, A, Bs, Cs, Ds, delta_bias, delta_softplus=True, out_dtype=torch.float32, need_states=True,
+                 y=None, states=None):
+    """One launch of the fused forward kernel (C ABI ``xfs_ss2d_fwd``) on contiguous, already validated tensors.
+    ``y`` / ``states`` may be passed to reuse buffers (CUDA-graph capture, benchmarks)."""
+    Bsz, D, H, W = x.shape
+    L, N, dev = H * W, Bs.shape[2], x.device
+    if y is None:
+        y = torch.empty((Bsz, D, L), dtype=out_dtype, device=dev)
+    if states is None and need_states:
+        states = torch.empty((Bsz, 4 * D, _lib.num_chunks(L), N), dtype=torch.float32, device=dev)
+    if y.numel():
+        args = _lib.Ss2dFwdArgs(_lib.ptr(x), _lib.ptr(delta), _lib.ptr(A), _lib.ptr(Bs), _lib.ptr(Cs), _lib.ptr(Ds),
+                                _lib.ptr(delta_bias), _lib.ptr(y), _lib.ptr(states), Bsz, D, N, H, W,
+                                _lib.dtype_code(x), _lib.dtype_code(y), int(bool(delta_softplus)), 0)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().xfs_ss2d_fwd(args, _lib.stream(dev))
+        _lib.check(rc, "ss2d_fwd")
+    return y, states
+
+
+def ss2d_bwd_raw(x, delta, A, Bs, Cs, Ds, delta_bias, dy, states, delta_softplus=True, out=None, zero=True):
+    """One launch of the fused backward kernel (C ABI ``xfs_ss2d_bwd``).  Returns (dx, ddelta, dA, dBs, dCs, dDs,
+    ddelta_bias) with dBs/dCs as the fp32 accumulators.  ``out`` may carry those 7 buffers for reuse; the accumulated
+    ones are zero-filled here (stream-ordered memsets) unless ``zero=False`` (caller already did), as the reference host
+    code does (selective_scan.cpp:331-337)."""
+    Bsz, D, H, W = x.shape
+    N, dev = Bs.shape[2], x.device
+    if out is None:
+        out = (torch.empty_like(x), torch.empty_like(delta), torch.empty_like(A),
+               torch.empty(Bs.shape, dtype=torch.float32, device=dev), torch.empty(Cs.shape, dtype=torch.float32, device=dev),
+               None if Ds is None else torch.empty_like(Ds), None if delta_bias is None else torch.empty_like(delta_bias))
+    dx, ddelta, dA, dBs, dCs, dDs, dbias = out
+    if zero:
+        for acc in (dA, dBs, dCs, dDs, dbias):
+            if acc is not None:
+                acc.zero_()
+    if x.numel():
+        args = _lib.Ss2dBwdArgs(_lib.ptr(x), _lib.ptr(delta), _lib.ptr(A), _lib.ptr(Bs), _lib.ptr(Cs), _lib.ptr(Ds),
+                                _lib.ptr(delta_bias), _lib.ptr(dy), _lib.ptr(states), _lib.ptr(dx), _lib.ptr(ddelta),
+                                _lib.ptr(dA), _lib.ptr(dBs), _lib.ptr(dCs), _lib.ptr(dDs), _lib.ptr(dbias),
+                                Bsz, D, N, H, W, _lib.dtype_code(x), _lib.dtype_code(dy), int(bool(delta_softplus)), 0)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().xfs_ss2d_bwd(args, _lib.stream(dev))
+        _lib.check(rc, "ss2d_bwd")
+    return dx, ddelta, dA, dBs, dCs, dDs, dbias
+
+
 class SS2DScanFn(torch.autograd.Function):
     """y = cross_merge(selective_scan(cross_scan(x), delta, A, Bs, Cs, Ds, delta_bias)), all four routes in one kernel."""
 
@@ -144,15 +191,7 @@ class SS2DScanFn(torch.autograd.Function):
         delta_bias = None if delta_bias is None else delta_bias.contiguous()
         out_dtype = torch.float32 if oflex else x.dtype
         if fused:
-            y = torch.empty((Bsz, D, L), dtype=out_dtype, device=dev)
-            states = torch.empty((Bsz, 4 * D, _lib.num_chunks(L), N), dtype=torch.float32, device=dev) if need else None
-            if y.numel():
-                args = _lib.Ss2dFwdArgs(_lib.ptr(x), _lib.ptr(delta), _lib.ptr(A), _lib.ptr(Bs), _lib.ptr(Cs), _lib.ptr(Ds),
-                                        _lib.ptr(delta_bias), _lib.ptr(y), _lib.ptr(states), Bsz, D, N, H, W,
-                                        _lib.dtype_code(x), _lib.dtype_code(y), int(bool(delta_softplus)), 0)
-                with torch.cuda.device(dev):
-                    rc = _lib.lib().xfs_ss2d_fwd(args, _lib.stream(dev))
-                _lib.check(rc, "ss2d_fwd")
+            y, states = ss2d_fwd_raw(x, delta, A, Bs, Cs, Ds, delta_bias, delta_softplus, out_dtype, need)
         else:
             xs = cross_scan_raw(x).view(Bsz, 4 * D, L)
             ys, states, _ = selective_scan_fwd_raw(xs, delta, A, Bs, Cs, Ds, delta_bias, delta_softplus, oflex, need_states=need)
@@ -180,21 +219,7 @@ class SS2DScanFn(torch.autograd.Function):
         if dy.dtype not in (torch.float32, x.dtype):
             dy = dy.to(x.dtype)
         if ctx.fused:
-            dx = torch.empty_like(x)
-            ddelta = torch.empty_like(delta)
-            dA = torch.zeros_like(A)
-            dBs = torch.zeros(Bs.shape, dtype=torch.float32, device=dev)
-            dCs = torch.zeros(Cs.shape, dtype=torch.float32, device=dev)
-            dDs = None if Ds is None else torch.zeros_like(Ds)
-            dbias = None if delta_bias is None else torch.zeros_like(delta_bias)
-            if x.numel():
-                args = _lib.Ss2dBwdArgs(_lib.ptr(x), _lib.ptr(delta), _lib.ptr(A), _lib.ptr(Bs), _lib.ptr(Cs), _lib.ptr(Ds),
-                                        _lib.ptr(delta_bias), _lib.ptr(dy), _lib.ptr(states), _lib.ptr(dx), _lib.ptr(ddelta),
-                                        _lib.ptr(dA), _lib.ptr(dBs), _lib.ptr(dCs), _lib.ptr(dDs), _lib.ptr(dbias),
-                                        Bsz, D, N, H, W, _lib.dtype_code(x), _lib.dtype_code(dy), int(bool(ctx.delta_softplus)), 0)
-                with torch.cuda.device(dev):
-                    rc = _lib.lib().xfs_ss2d_bwd(args, _lib.stream(dev))
-                _lib.check(rc, "ss2d_bwd")
+            dx, ddelta, dA, dBs, dCs, dDs, dbias = ss2d_bwd_raw(x, delta, A, Bs, Cs, Ds, delta_bias, dy, states, ctx.delta_softplus)
             dBs, dCs = dBs.to(Bs.dtype), dCs.to(Cs.dtype)
         else:
             xs = cross_scan_raw(x).view(Bsz, 4 * D, L)
