@@ -82,9 +82,14 @@ __device__ __forceinline__ void stg16(void* p, uint4 v) { *reinterpret_cast<uint
 
 // Load elements [l0, l0+8) of a row of length L into v (positions >= L or < 0 get `fill`).  `vec_ok` says the row
 // base is 16-byte aligned and L is a multiple of the vector width, so any in-range aligned group may be vector loaded.
-template <typename T>
+// kClampOutside: a lane whose 8 positions ALL lie outside the row reads elements 0..7 instead of getting `fill`
+// (keeps it on the vector path; callers must then neutralise those positions themselves -- the fused kernels do, by
+// forcing dt = 0 beyond L and never storing them).  Writing this as a third "fill" branch makes ptxas keep the
+// destination arrays in local memory, hence the clamp.
+template <typename T, bool kClampOutside = false>
 __device__ __forceinline__ void load8(const T* __restrict__ row, int64_t l0, int64_t L, bool vec_ok, float (&v)[8],
                                       float fill = 0.0f) {
+    if (kClampOutside && (l0 >= L || l0 + 8 <= 0)) l0 = 0;
     if (vec_ok && l0 >= 0 && l0 + 8 <= L) {
         if constexpr (Elem<T>::kVec == 4) {
             const uint4 a = ldg16(row + l0), b = ldg16(row + l0 + 4);
@@ -96,7 +101,7 @@ __device__ __forceinline__ void load8(const T* __restrict__ row, int64_t l0, int
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = Elem<T>::to_f(e[i]);
         }
-    } else {
+    } else {                                   // straddles an end of the row, or rows are not 16-byte aligned
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int64_t l = l0 + i;
@@ -142,19 +147,19 @@ __device__ __forceinline__ void reverse8(float (&v)[8]) {
 // Each lane first folds its kItems maps sequentially into (P, S) = (prod a, value of the fold started at 0).
 // warp_prefix then turns the per-lane folds into, for every lane, the state ENTERING that lane given the state
 // `carry` entering the chunk, and returns the state leaving the chunk (lane-uniform).  kRev walks lanes 31 -> 0.
-// 5 steps x (2 SHFL + FMUL + FFMA + 2 SEL).
+// 5 steps x (2 SHFL + predicated FFMA + FMUL).
 // ---------------------------------------------------------------------------------------------------------
 template <bool kRev>
 __device__ __forceinline__ float warp_prefix(float P, float S, float carry, int lane, float& chunk_out) {
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
-        float Pn = kRev ? __shfl_down_sync(kFull, P, off) : __shfl_up_sync(kFull, P, off);
-        float Sn = kRev ? __shfl_down_sync(kFull, S, off) : __shfl_up_sync(kFull, S, off);
+        const float Pn = kRev ? __shfl_down_sync(kFull, P, off) : __shfl_up_sync(kFull, P, off);
+        const float Sn = kRev ? __shfl_down_sync(kFull, S, off) : __shfl_up_sync(kFull, S, off);
         const bool has = kRev ? (lane + off < 32) : (lane >= off);
-        Pn = has ? Pn : 1.0f;
-        Sn = has ? Sn : 0.0f;
-        S = fmaf(P, Sn, S);   // apply the earlier maps first, then this lane's
-        P = P * Pn;
+        if (has) {             // predicated FFMA/FMUL: apply the earlier maps first, then this lane's
+            S = fmaf(P, Sn, S);
+            P = P * Pn;
+        }
     }
     // (P, S) is now the inclusive fold up to and including this lane
     const float incl = fmaf(P, carry, S);
