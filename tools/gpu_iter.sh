@@ -2,7 +2,7 @@
 # one optimisation iteration on the GPU box: parity tests (fused subset), bench line summary, optional ncu capture
 # usage: tools/gpu_iter.sh <tag> [ncu]
 TAG=${1:-iter}
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "ss2d or golden" 2>&1 | tail -3
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q  2>&1 | tail -3
 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err
 python - <<PY
 import json

@@ -1,24 +1,31 @@
-// ss2d_fused.cuh -- fused SS2D core for sm_100a: CrossScan gather + S6 selective scan + CrossMerge in ONE kernel
-// (forward) and the whole gradient in ONE kernel (backward).
+// ss2d_fused.cuh -- shared pieces of the fused SS2D kernels (ss2d_fwd.cu, ss2d_bwd.cu).
 //
-// Replaces the operator sequence of SS2Dv2.forward_corev2 (reference models/fusion_vmamba.py:1145,1170-1174):
+// The fused kernels replace the operator sequence of SS2Dv2.forward_corev2 (reference
+// models/fusion_vmamba.py:1145,1170-1174):
 //     xs = cross_scan_fn(x); ys = selective_scan_fn(xs, dts, As, Bs, Cs, Ds, delta_bias, True); y = cross_merge_fn(ys)
-// which moves ~22 elements per (b, d, l) through HBM (xs written 4x and re-read, ys written 4x and re-read).  Here x is
-// read once, delta/B/C are streamed once, the merged y is written once: 6 elements per (b, d, l) + B/C.
+// which moves ~22 elements per (b, d, l) through HBM (xs written 4x and re-read, ys written 4x and re-read).  Fused, x is
+// read once, delta/B/C are streamed once and the merged y is written once: 6 elements per (b, d, l) + B/C.
 //
-// Work decomposition
-//   CTA  = one batch image x kCh adjacent channels; 4 warps = the 4 routes, all running concurrently.
-//   The channels of a CTA share the B/C values of a route (they live in registers once per chunk).
-//   Shared memory holds, per channel, the image in row-major order (xN) and column-major order (xT) and the two
-//   accumulators yN (routes 0+2) and yT (routes 1+3), all indexed by POSITION (ss2d_tiles.cuh).
-//   Routes 2/3 walk the same position chunks as routes 0/1 but from the far end (reverse warp scan), so a route and
-//   its flip never touch the same accumulator chunk in the same half of the walk: the first half stores, then one
-//   64-thread named barrier, then the second half read-modify-writes what the partner stored.  No atomics, and the
-//   sum (y0 + y2) + (y1 + y3) is evaluated in the reference's order (models/csm_triton.py:61-62).
-//   The S6 recurrence h_l = exp(dt_l A) h_{l-1} + dt_l B_l u_l is scanned per 256-position chunk with a warp-shuffle
-//   scan of affine maps (xfscan_common.cuh), state carried in registers (N == 1) or shared memory (N > 1).
-//   delta/B/C of the NEXT chunk are loaded (128-bit, register double buffer) before the current chunk is computed, and
-//   the element-wise arithmetic runs on packed fp32 pairs (FFMA2/FMUL2/FADD2).
+// Work decomposition (both directions)
+//   CTA  = one batch image x kCh channel(s); 4 warps = the 4 CrossScan routes, all running concurrently.
+//   Shared memory holds, per channel, the image in row-major order (routes 0/2) and column-major order (routes 1/3)
+//   and one accumulator per orientation, all indexed by POSITION (ss2d_tiles.cuh).
+//   Routes 2/3 walk the same 256-position chunks as routes 0/1 but from the far end with a reversed warp scan, so a
+//   route and its flip never touch the same accumulator chunk in the same half of the walk: the first half stores,
+//   then ONE 64-thread named barrier, then the second half read-modify-writes what the partner stored.  No atomics,
+//   and the merge (y0 + y2) + (y1 + y3) is evaluated in the reference's order (models/csm_triton.py:61-62).
+//   The S6 recurrence h_l = exp(dt_l A) h_{l-1} + dt_l B_l u_l is scanned per chunk with a warp-shuffle scan of affine
+//   maps (xfscan_common.cuh); the state is carried in a register (N == 1) or in shared memory (N > 1).
+//   delta/B/C of the NEXT chunk are loaded (128-bit) into a second register set while the current chunk is computed;
+//   element-wise arithmetic runs on packed fp32 pairs (FFMA2/FMUL2/FADD2).
+//
+// Two things learned from ncu that shape the code:
+//   * ptxas tracks outstanding global loads with a few COUNTING scoreboards.  If the next chunk's loads are issued
+//     before the current chunk's load registers are first read, both batches can share a scoreboard and that first read
+//     waits ~1000 cycles for the loads just issued.  So each chunk first reads every load register once
+//     (dt -> dt + bias, B -> B*u, C -> C + 0), THEN issues the next loads.
+//   * scalar edge code inlined into the hot loops made the backward 127 KB of SASS and stall on instruction fetch.
+//     kFast kernels (rows 16-byte aligned, L a multiple of the vector width) contain no scalar edge code.
 #pragma once
 
 #include <cstdlib>
@@ -28,25 +35,22 @@
 
 namespace xfs {
 
-// channels per CTA (both variants are compiled; XFS_FWD_CH / XFS_BWD_CH override the default for experiments)
-inline int env_int(const char* name, int dflt) {
-    const char* v = std::getenv(name);
-    return v ? std::atoi(v) : dflt;
-}
-inline int fwd_ch() { static const int v = env_int("XFS_FWD_CH", 2) == 1 ? 1 : 2; return v; }
-inline int bwd_ch() { static const int v = env_int("XFS_BWD_CH", 1) == 2 ? 2 : 1; return v; }
 constexpr int kFusedMaxState = 64;           // states carried in smem for N > 1
+constexpr size_t kSmemLimit = 227 * 1024;
 
 __device__ __forceinline__ void pair_barrier(int pair) {   // the 2 warps of a route pair (routes k and k+2)
     asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory");
 }
-
 // CTA-wide barrier 0, issued from inside the two instantiations of the route walk (per-thread arrival on sm_70+)
 __device__ __forceinline__ void cta_barrier() { asm volatile("bar.sync 0;" ::: "memory"); }
 
 __device__ __forceinline__ void pack8(const float (&v)[8], f2 (&o)[4]) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) o[j] = make_float2(v[2 * j], v[2 * j + 1]);
+}
+__device__ __forceinline__ void unpack8(const f2 (&v)[4], float (&o)[8]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { o[2 * j] = v[j].x; o[2 * j + 1] = v[j].y; }
 }
 // address order -> position order (a flip for routes 2/3); never writes the source, so it is pure register renaming
 template <bool kRev>
@@ -55,23 +59,31 @@ __device__ __forceinline__ void to_pos(const float (&src)[8], float (&dst)[8]) {
     for (int i = 0; i < 8; ++i) dst[i] = src[kRev ? 7 - i : i];
 }
 
+// one 8-position row access of the streamed tensors; kFast: vector-only code (see load8_fast)
+template <typename T, bool kFast>
+__device__ __forceinline__ void row_load8(const T* __restrict__ row, int l0, int L, bool vec_ok, float (&v)[8]) {
+    if constexpr (kFast) load8_fast<T>(row, l0, L, v);
+    else load8<T, true>(row, l0, L, vec_ok, v);
+}
+template <typename T, bool kFast>
+__device__ __forceinline__ void row_store8(T* __restrict__ row, int l0, int L, bool vec_ok, const float (&v)[8]) {
+    if constexpr (kFast) store8_fast<T>(row, l0, L, v);
+    else store8<T>(row, l0, L, vec_ok, v);
+}
+
 inline size_t fwd_smem(int64_t L, int64_t N, int ch) {
     return sizeof(float) * (size_t)(4 * ch * buf_len(L) + (N == 1 ? 0 : 4 * ch * kFusedMaxState));
 }
 inline size_t bwd_smem(int64_t L, int64_t N, int ch) {
     return sizeof(float) * (size_t)(6 * ch * buf_len(L) + (N == 1 ? 0 : 2 * 4 * ch * kFusedMaxState));
 }
-// largest channel count per CTA (<= preferred) whose working set fits; 0 = none
-inline int fit_ch(int64_t L, int64_t N, int preferred, bool backward) {
-    for (int ch = preferred; ch >= 1; --ch)
-        if ((backward ? bwd_smem(L, N, ch) : fwd_smem(L, N, ch)) <= 227 * 1024) return ch;
-    return 0;
-}
-
 
 template <typename K>
 inline int set_smem(K kernel, size_t bytes) {
     return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
 }
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+__device__ __forceinline__ bool aligned16_dev(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace xfs

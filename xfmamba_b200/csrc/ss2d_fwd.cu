@@ -3,21 +3,19 @@
 
 namespace xfs {
 
-// =========================================================================================================
-// forward
-// =========================================================================================================
-template <typename T, int kN, int kCh>
-struct FwdChunk {            // raw inputs of one chunk of one route (position order)
+template <int kN, int kCh>
+struct FwdChunk {            // delta/B/C of one chunk of one route, in ADDRESS order, exactly as loaded
     float dt[kCh][8];
     float B[8], C[8];       // kN == 1 only
 };
 
-template <typename T, typename TO, int kN, int kCh>   // kN == 1: single state in registers; kN == 0: runtime N (<= kFusedMaxState)
+// kN == 1: single state carried in a register; kN == 0: runtime N (<= kFusedMaxState), states carried in smem
+template <typename T, typename TO, int kN, int kCh, bool kFast>
 __global__ void __launch_bounds__(128)
 ss2d_fwd_kernel(const xfs_ss2d_fwd_args p) {
     extern __shared__ __align__(16) float smem[];
     const int H = (int)p.H, W = (int)p.W, L = H * W;
-    const int Lb = (int)buf_len(L), nch = Lb / kChunk;
+    const int Lb = (int)buf_len(L), nch = (L + kChunk - 1) / kChunk;
     const int D = (int)p.D;
     const int N = (kN == 1) ? 1 : (int)p.N;
     const int groups = (D + kCh - 1) / kCh;
@@ -40,8 +38,8 @@ ss2d_fwd_kernel(const xfs_ss2d_fwd_args p) {
     const T* __restrict__ delta = reinterpret_cast<const T*>(p.delta);
     const T* __restrict__ Bk = reinterpret_cast<const T*>(p.Bs) + ((int64_t)b * 4 + k) * N * L;
     const T* __restrict__ Ck = reinterpret_cast<const T*>(p.Cs) + ((int64_t)b * 4 + k) * N * L;
-    const bool vin = row_vec_ok(delta, L) && row_vec_ok(reinterpret_cast<const T*>(p.Bs), L) &&
-                     row_vec_ok(reinterpret_cast<const T*>(p.Cs), L);
+    const bool vin = kFast || (row_vec_ok(delta, L) && row_vec_ok(reinterpret_cast<const T*>(p.Bs), L) &&
+                               row_vec_ok(reinterpret_cast<const T*>(p.Cs), L));
 
     const T* dt_row[kCh];
     float* st_row[kCh];
@@ -57,147 +55,176 @@ ss2d_fwd_kernel(const xfs_ss2d_fwd_args p) {
         A2_1[ch] = (kN == 1) ? p.A[kd[ch]] * kLog2e : 0.0f;
         carry1[ch] = 0.0f;
     }
+    const f2 rt_zero2 = splat2(__int_as_float(p.scans));   // +0.0f (scans == 0), but only known at run time
 
     const int m = (nch + 1) / 2;        // chunks [0, m) are first touched by the forward route, [m, nch) by its flip
     bool synced = false;
 
-    // The walk is instantiated twice (kRev = false for routes 0/1, true for their flips 2/3) so that the flip is pure
-    // register renaming instead of predicated moves.
+    // The walk is instantiated twice (rev = false for routes 0/1, true for their flips 2/3) so that the flip is pure
+    // register renaming (or an operand swizzle of the packed instructions) instead of predicated moves.
     auto walk = [&](auto rev_tag) __attribute__((always_inline)) {
-    constexpr bool rev = decltype(rev_tag)::value;
-    // delta/B/C of one chunk, kept in ADDRESS order: any use (even a register swap) would wait for the loads and
-    // defeat the double buffering, so the flip of routes 2/3 happens at compute time.
-    auto load_chunk = [&](int step, FwdChunk<T, kN, kCh>& c) __attribute__((always_inline)) {
-        const int j = rev ? (nch - 1 - step) : step;
-        const int p0 = j * kChunk + lane * kItems;
-        const int l0 = rev ? L - 8 - p0 : p0;            // scan index of the lowest-address element
-#pragma unroll
-        for (int ch = 0; ch < kCh; ++ch) load8<T, true>(dt_row[ch], l0, L, vin, c.dt[ch]);
-        if (kN == 1) {
-            load8<T, true>(Bk, l0, L, vin, c.B);
-            load8<T, true>(Ck, l0, L, vin, c.C);
-        }
-    };
-    FwdChunk<T, kN, kCh> ca, cb;
-    load_chunk(0, ca);                  // in flight while the image is staged
+        constexpr bool rev = decltype(rev_tag)::value;
 
-    {
-        const T* __restrict__ x = reinterpret_cast<const T*>(p.x);
+        auto load_chunk = [&](int step, FwdChunk<kN, kCh>& c) __attribute__((always_inline)) {
+            const int j = rev ? (nch - 1 - step) : step;
+            const int p0 = j * kChunk + lane * kItems;
+            const int l0 = rev ? L - 8 - p0 : p0;        // scan index of the lowest-address element
 #pragma unroll
-        for (int ch = 0; ch < kCh; ++ch)
-            stage_image<T>(x + ((int64_t)b * D + (valid[ch] ? d0 + ch : d0)) * L, xN + ch * Lb, xT + ch * Lb, H, W, L, Lb, valid[ch], tid, 128);
-        if (kN == 0)
-            for (int i = tid; i < 4 * kCh * kFusedMaxState; i += 128) s_h[i] = 0.0f;
-        cta_barrier();                  // all 4 warps arrive here, two from each instantiation of the walk
-    }
-    auto compute_chunk = [&](int step, FwdChunk<T, kN, kCh>& c) __attribute__((always_inline)) {
-        const int j = rev ? (nch - 1 - step) : step;
-        const int p0 = j * kChunk + lane * kItems;
-        const int l0 = rev ? L - 8 - p0 : p0;
-        const int f4s = swz_f4(p0 >> 2);
-        const bool tail = p0 + 8 > L;
-
-        f2 dt2[kCh][4], u2[kCh][4], y2[kCh][4];
-#pragma unroll
-        for (int ch = 0; ch < kCh; ++ch) {
-            float u[8];
-            lds8(xb + ch * Lb, f4s, u);
-            pack8(u, u2[ch]);
-            float dtp[8];
-            to_pos<rev>(c.dt[ch], dtp);
-            pack8(dtp, dt2[ch]);
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const f2 xx = add2(dt2[ch][jj], splat2(bias[ch]));
-                f2 e;
-                dt2[ch][jj] = p.delta_softplus ? softplus2(xx, e) : xx;
-                y2[ch][jj] = mul2(splat2(Dd[ch]), u2[ch][jj]);
-            }
-            if (tail) {                                   // positions >= L: identity map (dt = 0)
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    if (p0 + 2 * jj >= L) dt2[ch][jj].x = 0.0f;
-                    if (p0 + 2 * jj + 1 >= L) dt2[ch][jj].y = 0.0f;
-                }
-            }
-        }
-        for (int n = 0; n < N; ++n) {
-            f2 B2[4], C2[4];
+            for (int ch = 0; ch < kCh; ++ch) row_load8<T, kFast>(dt_row[ch], l0, L, vin, c.dt[ch]);
             if (kN == 1) {
-                float Bp[8], Cp[8];
-                to_pos<rev>(c.B, Bp); to_pos<rev>(c.C, Cp);
-                pack8(Bp, B2); pack8(Cp, C2);
+                row_load8<T, kFast>(Bk, l0, L, vin, c.B);
+                row_load8<T, kFast>(Ck, l0, L, vin, c.C);
             }
-            else {
-                float Bv[8], Cv[8];
-                load8<T, true>(Bk + n * L, l0, L, vin, Bv);
-                load8<T, true>(Ck + n * L, l0, L, vin, Cv);
-                if (rev) { reverse8(Bv); reverse8(Cv); }
-                pack8(Bv, B2); pack8(Cv, C2);
-            }
+        };
+
+        FwdChunk<kN, kCh> ca, cb;
+        load_chunk(0, ca);              // in flight while the image is staged
+        {
+            const T* __restrict__ x = reinterpret_cast<const T*>(p.x);
+#pragma unroll
+            for (int ch = 0; ch < kCh; ++ch)
+                stage_image<T>(x + ((int64_t)b * D + (valid[ch] ? d0 + ch : d0)) * L, xN + ch * Lb, xT + ch * Lb, H, W, L, Lb,
+                               valid[ch], tid, 128);
+            if (kN == 0)
+                for (int i = tid; i < 4 * kCh * kFusedMaxState; i += 128) s_h[i] = 0.0f;
+            cta_barrier();              // all 4 warps arrive here, two from each instantiation of the walk
+        }
+
+        auto compute_chunk = [&](int step, FwdChunk<kN, kCh>& c, auto&& issue_next) __attribute__((always_inline)) {
+            const int j = rev ? (nch - 1 - step) : step;
+            const int p0 = j * kChunk + lane * kItems;
+            const int l0 = rev ? L - 8 - p0 : p0;
+            const int f4s = swz_f4(p0 >> 2);
+            const bool in_buf = p0 < Lb;                    // lane has shared-memory backing
+            const bool tail = p0 + 8 > L;
+
+            // ---- read every load register once, then issue the next chunk's loads (scoreboard note in the header)
+            f2 dt2[kCh][4], u2[kCh][4], y2[kCh][4], Bu2[kCh][4], C1[4];
 #pragma unroll
             for (int ch = 0; ch < kCh; ++ch) {
-                const float A2 = (kN == 1) ? A2_1[ch] : p.A[kd[ch] * N + n] * kLog2e;
-                f2 a2[4], bu2[4], S2[4], P2[4];
+                float u[8];
+                if (in_buf) lds8(xb + ch * Lb, f4s, u);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) u[i] = 0.0f;
+                }
+                pack8(u, u2[ch]);
+                float dtp[8];
+                to_pos<rev>(c.dt[ch], dtp);
+                pack8(dtp, dt2[ch]);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) dt2[ch][jj] = add2(dt2[ch][jj], splat2(bias[ch]));
+            }
+            if (kN == 1) {
+                float Bp[8], Cp[8];
+                f2 B1[4];
+                to_pos<rev>(c.B, Bp); to_pos<rev>(c.C, Cp);
+                pack8(Bp, B1); pack8(Cp, C1);
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
-                    a2[jj] = ex2_2(mul2(dt2[ch][jj], splat2(A2)));
-                    bu2[jj] = mul2(mul2(dt2[ch][jj], B2[jj]), u2[ch][jj]);
+                    C1[jj] = add2(C1[jj], rt_zero2);
+#pragma unroll
+                    for (int ch = 0; ch < kCh; ++ch) Bu2[ch][jj] = mul2(B1[jj], u2[ch][jj]);
                 }
-                float Pr = 1.0f, Sr = 0.0f;
-                if (!rev) {
+            }
+            issue_next();
+
+            // ---- dt = softplus(delta + bias); y starts as D*u
+#pragma unroll
+            for (int ch = 0; ch < kCh; ++ch) {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const f2 xx = dt2[ch][jj];
+                    f2 e;
+                    dt2[ch][jj] = p.delta_softplus ? softplus2(xx, e) : xx;
+                    y2[ch][jj] = mul2(splat2(Dd[ch]), u2[ch][jj]);
+                }
+                if (tail) {                                   // positions >= L: identity map (dt = 0)
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
-                        Sr = fmaf(a2[jj].x, Sr, bu2[jj].x); Pr *= a2[jj].x; S2[jj].x = Sr; P2[jj].x = Pr;
-                        Sr = fmaf(a2[jj].y, Sr, bu2[jj].y); Pr *= a2[jj].y; S2[jj].y = Sr; P2[jj].y = Pr;
-                    }
-                } else {
-#pragma unroll
-                    for (int jj = 3; jj >= 0; --jj) {
-                        Sr = fmaf(a2[jj].y, Sr, bu2[jj].y); Pr *= a2[jj].y; S2[jj].y = Sr; P2[jj].y = Pr;
-                        Sr = fmaf(a2[jj].x, Sr, bu2[jj].x); Pr *= a2[jj].x; S2[jj].x = Sr; P2[jj].x = Pr;
+                        if (p0 + 2 * jj >= L) dt2[ch][jj].x = 0.0f;
+                        if (p0 + 2 * jj + 1 >= L) dt2[ch][jj].y = 0.0f;
                     }
                 }
-                float* hs = s_h + (k * kCh + ch) * kFusedMaxState + n;
-                const float carry = (kN == 1) ? carry1[ch] : *hs;
-                float h_out;
-                const float h_in = rev ? warp_prefix<true>(Pr, Sr, carry, lane, h_out)
-                                       : warp_prefix<false>(Pr, Sr, carry, lane, h_out);
-                const f2 hin2 = splat2(h_in);
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) y2[ch][jj] = fma2(C2[jj], fma2(P2[jj], hin2, S2[jj]), y2[ch][jj]);
-                if (kN == 1) carry1[ch] = h_out;
-                else { __syncwarp(); if (lane == 0) *hs = h_out; }
-                if (st_row[ch] && lane == 0) st_row[ch][j * N + n] = h_out;
             }
-        }
-        // accumulate into the pair's buffer
-        const bool first_touch = rev ? (j >= m) : (j < m);
-        if (!first_touch && !synced) { pair_barrier(k & 1); synced = true; }
+            for (int n = 0; n < N; ++n) {
+                f2 C2[4];
+                if (kN == 1) {
 #pragma unroll
-        for (int ch = 0; ch < kCh; ++ch) {
-            float* yc = yb + ch * Lb;
-            float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
-            if (!first_touch) {
-                o0 = *reinterpret_cast<const float4*>(yc + (f4s << 2));
-                o1 = *reinterpret_cast<const float4*>(yc + ((f4s ^ 1) << 2));
+                    for (int jj = 0; jj < 4; ++jj) C2[jj] = C1[jj];
+                } else {
+                    float Bv[8], Cv[8], Bp[8], Cp[8];
+                    f2 B2[4];
+                    row_load8<T, kFast>(Bk + n * L, l0, L, vin, Bv);
+                    row_load8<T, kFast>(Ck + n * L, l0, L, vin, Cv);
+                    to_pos<rev>(Bv, Bp); to_pos<rev>(Cv, Cp);
+                    pack8(Bp, B2); pack8(Cp, C2);
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                        for (int ch = 0; ch < kCh; ++ch) Bu2[ch][jj] = mul2(B2[jj], u2[ch][jj]);
+                }
+#pragma unroll
+                for (int ch = 0; ch < kCh; ++ch) {
+                    const float A2 = (kN == 1) ? A2_1[ch] : p.A[kd[ch] * N + n] * kLog2e;
+                    f2 a2[4], bu2[4], S2[4], P2[4];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        a2[jj] = ex2_2(mul2(dt2[ch][jj], splat2(A2)));
+                        bu2[jj] = mul2(dt2[ch][jj], Bu2[ch][jj]);
+                    }
+                    float Pr = 1.0f, Sr = 0.0f;
+                    if (!rev) {
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            Sr = fmaf(a2[jj].x, Sr, bu2[jj].x); Pr *= a2[jj].x; S2[jj].x = Sr; P2[jj].x = Pr;
+                            Sr = fmaf(a2[jj].y, Sr, bu2[jj].y); Pr *= a2[jj].y; S2[jj].y = Sr; P2[jj].y = Pr;
+                        }
+                    } else {
+#pragma unroll
+                        for (int jj = 3; jj >= 0; --jj) {
+                            Sr = fmaf(a2[jj].y, Sr, bu2[jj].y); Pr *= a2[jj].y; S2[jj].y = Sr; P2[jj].y = Pr;
+                            Sr = fmaf(a2[jj].x, Sr, bu2[jj].x); Pr *= a2[jj].x; S2[jj].x = Sr; P2[jj].x = Pr;
+                        }
+                    }
+                    float* hs = s_h + (k * kCh + ch) * kFusedMaxState + n;
+                    const float carry = (kN == 1) ? carry1[ch] : *hs;
+                    float h_out;
+                    const float h_in = warp_prefix<rev>(Pr, Sr, carry, lane, h_out);
+                    const f2 hin2 = splat2(h_in);
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) y2[ch][jj] = fma2(C2[jj], fma2(P2[jj], hin2, S2[jj]), y2[ch][jj]);
+                    if (kN == 1) carry1[ch] = h_out;
+                    else { __syncwarp(); if (lane == 0) *hs = h_out; }
+                    if (st_row[ch] && lane == 0) st_row[ch][j * N + n] = h_out;
+                }
             }
-            const f2 r0 = add2(y2[ch][0], make_float2(o0.x, o0.y)), r1 = add2(y2[ch][1], make_float2(o0.z, o0.w));
-            const f2 r2 = add2(y2[ch][2], make_float2(o1.x, o1.y)), r3 = add2(y2[ch][3], make_float2(o1.z, o1.w));
-            *reinterpret_cast<float4*>(yc + (f4s << 2)) = make_float4(r0.x, r0.y, r1.x, r1.y);
-            *reinterpret_cast<float4*>(yc + ((f4s ^ 1) << 2)) = make_float4(r2.x, r2.y, r3.x, r3.y);
-        }
-    };
+            // ---- accumulate into the pair's buffer
+            const bool first_touch = rev ? (j >= m) : (j < m);
+            if (!first_touch && !synced) { pair_barrier(k & 1); synced = true; }
+            if (in_buf) {
+#pragma unroll
+                for (int ch = 0; ch < kCh; ++ch) {
+                    float* yc = yb + ch * Lb;
+                    float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+                    if (!first_touch) {
+                        o0 = *reinterpret_cast<const float4*>(yc + (f4s << 2));
+                        o1 = *reinterpret_cast<const float4*>(yc + ((f4s ^ 1) << 2));
+                    }
+                    const f2 r0 = add2(y2[ch][0], make_float2(o0.x, o0.y)), r1 = add2(y2[ch][1], make_float2(o0.z, o0.w));
+                    const f2 r2 = add2(y2[ch][2], make_float2(o1.x, o1.y)), r3 = add2(y2[ch][3], make_float2(o1.z, o1.w));
+                    *reinterpret_cast<float4*>(yc + (f4s << 2)) = make_float4(r0.x, r0.y, r1.x, r1.y);
+                    *reinterpret_cast<float4*>(yc + ((f4s ^ 1) << 2)) = make_float4(r2.x, r2.y, r3.x, r3.y);
+                }
+            }
+        };
 
 #pragma unroll 1
-    for (int step = 0; step < nch; step += 2) {
-        if (step + 1 < nch) load_chunk(step + 1, cb);
-        compute_chunk(step, ca);
-        if (step + 1 < nch) {
-            if (step + 2 < nch) load_chunk(step + 2, ca);
-            compute_chunk(step + 1, cb);
+        for (int step = 0; step < nch; step += 2) {
+            compute_chunk(step, ca, [&]() __attribute__((always_inline)) { if (step + 1 < nch) load_chunk(step + 1, cb); });
+            if (step + 1 < nch)
+                compute_chunk(step + 1, cb, [&]() __attribute__((always_inline)) { if (step + 2 < nch) load_chunk(step + 2, ca); });
         }
-    }
     };  // walk
     if (k >= 2) walk(std::true_type{}); else walk(std::false_type{});
     if (!synced) pair_barrier(k & 1);
@@ -210,29 +237,37 @@ ss2d_fwd_kernel(const xfs_ss2d_fwd_args p) {
         if (valid[ch]) merge_out<TO>(out + ((int64_t)b * D + d0 + ch) * L, yN + ch * Lb, yT + ch * Lb, H, W, tid, 128);
 }
 
-// ---- host side
+// ---- host side --------------------------------------------------------------------------------------------------
+constexpr int kChFwd = 1;    // measured on B200 (config-2 shape): 1 channel/CTA (4 CTAs/SM) beats 2 (B/C shared, 2 CTAs/SM)
+
 int ss2d_supported(int64_t D, int64_t N, int64_t H, int64_t W, int dtype, int backward) {
     (void)D; (void)dtype;
     if (N < 1 || N > kFusedMaxState) return 0;
     const int64_t L = H * W;
     if (L <= 0 || L > (1 << 24)) return 0;
-    return fit_ch(L, N, backward ? bwd_ch() : fwd_ch(), backward != 0) > 0;
+    return (backward ? bwd_smem(L, N, 1) : fwd_smem(L, N, kChFwd)) <= kSmemLimit;
 }
 
-template <typename T, typename TO, int kN, int kCh>
+template <typename T, typename TO, int kN, bool kFast>
 static int launch_fwd_k(const xfs_ss2d_fwd_args& a, cudaStream_t st) {
-    const size_t smem = fwd_smem(a.H * a.W, a.N, kCh);
-    const unsigned grid = (unsigned)(a.batch * ((a.D + kCh - 1) / kCh));
-    if (int rc = set_smem(ss2d_fwd_kernel<T, TO, kN, kCh>, smem)) return rc;
-    ss2d_fwd_kernel<T, TO, kN, kCh><<<grid, 128, smem, st>>>(a);
+    const size_t smem = fwd_smem(a.H * a.W, a.N, kChFwd);
+    const unsigned grid = (unsigned)(a.batch * ((a.D + kChFwd - 1) / kChFwd));
+    if (int rc = set_smem(ss2d_fwd_kernel<T, TO, kN, kChFwd, kFast>, smem)) return rc;
+    ss2d_fwd_kernel<T, TO, kN, kChFwd, kFast><<<grid, 128, smem, st>>>(a);
     return check_launch();
 }
 
 template <typename T, typename TO>
 static int launch_fwd_tt(const xfs_ss2d_fwd_args& a, cudaStream_t st) {
-    const int ch = fit_ch(a.H * a.W, a.N, fwd_ch(), false);
-    if (a.N == 1) return ch == 2 ? launch_fwd_k<T, TO, 1, 2>(a, st) : launch_fwd_k<T, TO, 1, 1>(a, st);
-    return ch == 2 ? launch_fwd_k<T, TO, 0, 2>(a, st) : launch_fwd_k<T, TO, 0, 1>(a, st);
+    const int64_t L = a.H * a.W;
+    // fast rows: 16-byte aligned tensors and L a multiple of the vector width -> kernels without scalar edge code.
+    // Only instantiated for fp32 output (oflex, what XFMamba uses); anything else takes the general kernels.
+    const bool fast = std::is_same<TO, float>::value && (L % Elem<T>::kVec == 0) && aligned16(a.delta) && aligned16(a.Bs) &&
+                      aligned16(a.Cs);
+    if constexpr (std::is_same<TO, float>::value) {
+        if (fast) return a.N == 1 ? launch_fwd_k<T, TO, 1, true>(a, st) : launch_fwd_k<T, TO, 0, true>(a, st);
+    }
+    return a.N == 1 ? launch_fwd_k<T, TO, 1, false>(a, st) : launch_fwd_k<T, TO, 0, false>(a, st);
 }
 
 int launch_ss2d_fwd(const xfs_ss2d_fwd_args& a, cudaStream_t st) {

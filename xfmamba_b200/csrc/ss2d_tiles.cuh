@@ -15,7 +15,9 @@ namespace xfs {
 __device__ __forceinline__ int swz_f4(int f) { return f ^ ((f >> 3) & 7); }
 __device__ __forceinline__ int swz_pos(int p) { return (swz_f4(p >> 2) << 2) | (p & 3); }
 
-__host__ __device__ inline int64_t buf_len(int64_t L) { return ((L + kChunk - 1) / kChunk) * kChunk; }
+// buffer length: L rounded up to the swizzle period (32 floats); lanes whose 8 positions start at or beyond it skip
+// shared memory altogether
+__host__ __device__ inline int64_t buf_len(int64_t L) { return ((L + 31) / 32) * 32; }
 
 // lane's 8 consecutive positions starting at granule f4s (already swizzled); the partner granule is f4s ^ 1
 __device__ __forceinline__ void lds8(const float* buf, int f4s, float (&v)[8]) {

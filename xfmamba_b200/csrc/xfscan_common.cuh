@@ -132,6 +132,44 @@ __device__ __forceinline__ void store8(T* __restrict__ row, int64_t l0, int64_t 
     }
 }
 
+// ---- "fast rows": every row starts 16-byte aligned and L is a multiple of the 16-byte vector width, so each 16-byte
+// granule of a lane's 8 positions is either entirely inside the row or entirely outside.  No scalar edge code at all
+// (it would otherwise be inlined into every hot loop and blow the instruction cache).  Granules outside the row are
+// read from offset 0 instead (garbage the caller neutralises, see kClampOutside above) and never written.
+template <typename T>
+__device__ __forceinline__ void load8_fast(const T* __restrict__ row, int l0, int L, float (&v)[8]) {
+    if constexpr (Elem<T>::kVec == 4) {
+        const int g0 = (l0 >= 0 && l0 + 4 <= L) ? l0 : 0, g1 = (l0 + 4 >= 0 && l0 + 8 <= L) ? l0 + 4 : 0;
+        const uint4 a = ldg16(row + g0), b = ldg16(row + g1);
+        v[0] = __uint_as_float(a.x); v[1] = __uint_as_float(a.y); v[2] = __uint_as_float(a.z); v[3] = __uint_as_float(a.w);
+        v[4] = __uint_as_float(b.x); v[5] = __uint_as_float(b.y); v[6] = __uint_as_float(b.z); v[7] = __uint_as_float(b.w);
+    } else {
+        const int g0 = (l0 >= 0 && l0 + 8 <= L) ? l0 : 0;
+        const uint4 a = ldg16(row + g0);
+        const T* e = reinterpret_cast<const T*>(&a);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = Elem<T>::to_f(e[i]);
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void store8_fast(T* __restrict__ row, int l0, int L, const float (&v)[8]) {
+    if constexpr (Elem<T>::kVec == 4) {
+        if (l0 >= 0 && l0 + 4 <= L)
+            stg16(row + l0, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));
+        if (l0 + 4 >= 0 && l0 + 8 <= L)
+            stg16(row + l0 + 4, make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
+    } else {
+        if (l0 >= 0 && l0 + 8 <= L) {
+            uint4 a;
+            T* e = reinterpret_cast<T*>(&a);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) e[i] = Elem<T>::from_f(v[i]);
+            stg16(row + l0, a);
+        }
+    }
+}
+
 template <typename T> __device__ __forceinline__ bool row_vec_ok(const T* base, int64_t L) {
     return (L % Elem<T>::kVec == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
 }
