@@ -233,6 +233,50 @@ def gen_cores(ref):
     save("cores", **out)
 
 
+def gen_model(ref):
+    """a miniature TwoViewXFMambaTop (same classes, same forward code, small dims) -> weights, inputs, logits and a few
+    gradients.  The reference constructor hard-codes the three published sizes, so the object is assembled from the
+    reference's own building blocks and driven through the reference's unmodified ``TwoViewXFMambaTop.forward``."""
+    import torch.nn as nn
+    from collections import OrderedDict
+    net = _refload.load_net()
+    fv = ref.fusion_vmamba
+    torch.manual_seed(0)
+    hidden = 64
+    m = net.TwoViewXFMambaTop.__new__(net.TwoViewXFMambaTop)
+    nn.Module.__init__(m)
+    m.mamba_feature_extrac = fv.Backbone_VSSM(depths=[1, 1, 2, 1], dims=8, drop_path_rate=0.0, ssm_ratio=2.0)
+    m.shallow_mamba_fusion = fv.ShallowFusionBlock_v4(hidden_dim=hidden, attn_drop_rate=0.0, d_state=16)
+    m.fusemamba = fv.CSSFVSSLayer_v5(hidden_dim=hidden, depth=1, drop_path=[0.0], attn_drop_rate=0.0, d_state=16,
+                                     attention_downsampling=4)
+    m.final_conv = nn.Conv2d(hidden, hidden, kernel_size=1)
+    m.classifier = nn.Sequential(OrderedDict(avgpool=nn.AdaptiveAvgPool2d(1), flatten=nn.Flatten(1), head=nn.Linear(hidden, 3)))
+    with torch.no_grad():       # de-trivialise A / D / BatchNorm statistics
+        for name, p_ in m.named_parameters():
+            if name.endswith("A_logs") or name.endswith("Ds"):
+                p_.add_(0.2 * torch.randn_like(p_))
+        bn = m.shallow_mamba_fusion.norm
+        bn.running_mean.normal_(0, 0.3)
+        bn.running_var.uniform_(0.5, 1.5)
+    m.eval()
+    xa = torch.randn(2, 1, 96, 80)
+    xb = torch.randn(2, 1, 96, 80)
+    logits = m(xa, xb)
+    g = torch.randn(logits.shape)
+    (logits * g).sum().backward()
+    out = {"sd::" + k: npy(v) for k, v in m.state_dict().items()}
+    grad_names = ["classifier.head.weight", "mamba_feature_extrac.layers.0.blocks.0.op.A_logs",
+                  "mamba_feature_extrac.layers.0.blocks.0.op.x_proj_weight", "mamba_feature_extrac.layers.2.blocks.1.op.dt_projs_bias",
+                  "mamba_feature_extrac.patch_embed.0.weight", "shallow_mamba_fusion.shallowfuseSS2D.Ds",
+                  "shallow_mamba_fusion.shallowfuseSS2D.x_proj_weight", "fusemamba.blocks.0.self_attention.A_logs",
+                  "fusemamba.blocks.0.self_attention.dt_projs_weight", "fusemamba.blocks.0.self_attention.in_proj_sec.weight"]
+    params = dict(m.named_parameters())
+    for n_ in grad_names:
+        out["grad::" + n_] = npy(params[n_].grad)
+    out.update(xa=npy(xa), xb=npy(xb), logits=npy(logits), glogits=npy(g))
+    save("model_mini", **out)
+
+
 if __name__ == "__main__":
     ref = _refload.load()
     torch.set_num_threads(1)          # deterministic reductions
@@ -240,3 +284,4 @@ if __name__ == "__main__":
     gen_scan(ref)
     gen_swap(ref)
     gen_cores(ref)
+    gen_model(ref)
