@@ -339,10 +339,18 @@ def main():
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step (2 images = 1 two-view pair)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="ss2d", help="ss2d (default, BASELINE config 2) or xfmamba_{t,s,b}_infer / "
+                    "xfmamba_{s,b}_train / xfmamba_b_hires (end-to-end model, configs 3-5; see bench_model.py)")
+    ap.add_argument("--no-graph", action="store_true", help="model inference workloads: eager instead of a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "ss2d":
+        import bench_model
+        if args.batch == 64 and args.workload.endswith("train"):
+            args.batch = 32
+        bench_model.run(args, ClockSampler)
     else:
         run_ours(args)
 

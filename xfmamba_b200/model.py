@@ -188,7 +188,8 @@ class Backbone(nn.Module):
         super().__init__()
         dims = [dims * 2 ** i for i in range(len(depths))]
         self.dims = dims
-        dpr = torch.linspace(0, drop_path_rate, sum(depths)).tolist()
+        n_blocks = sum(depths)        # stochastic-depth rates rise linearly over the blocks (reference :1385)
+        dpr = [drop_path_rate * i / max(n_blocks - 1, 1) for i in range(n_blocks)]
         self.patch_embed = nn.Sequential(
             nn.Conv2d(in_chans, dims[0] // 2, 3, 2, 1), nn.Identity(), LayerNorm2d(dims[0] // 2), nn.Identity(), nn.GELU(),
             nn.Conv2d(dims[0] // 2, dims[0], 3, 2, 1), nn.Identity(), LayerNorm2d(dims[0]))
