@@ -159,6 +159,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from xfmamba_b200 import _lib, fusion_ops, ss2d_scan
+    from xfmamba_b200.dp import FlatBucket
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -186,7 +187,7 @@ def run_ours(args):
     grads = (torch.empty_like(d["x"]), torch.empty_like(d["delta"]), torch.empty_like(d["A"]),
              torch.empty(d["Bs"].shape, dtype=torch.float32, device=dev), torch.empty(d["Cs"].shape, dtype=torch.float32, device=dev),
              torch.empty_like(d["Ds"]), torch.empty_like(d["delta_bias"]))
-    flat = torch.empty(d["A"].numel() + d["Ds"].numel() + d["delta_bias"].numel(), dtype=torch.float32, device=dev)
+    bucket = FlatBucket([grads[2], grads[5], grads[6]])      # dA, dDs, ddelta_bias: the parameter gradients
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     fwd_ev, bwd_ev = [], []
@@ -208,9 +209,9 @@ def run_ours(args):
             e2.record()
             fwd_ev.append((e0, e1))
             bwd_ev.append((e1b, e2))
-        if world > 1:   # data-parallel exchange of the parameter gradients (training step)
-            torch.cat([grads[2].reshape(-1), grads[5], grads[6]], out=flat)
-            dist.all_reduce(flat)
+        if world > 1:   # data-parallel exchange of the parameter gradients (training step): one NCCL all-reduce
+            bucket.pack([grads[2], grads[5], grads[6]])
+            bucket.allreduce(average=True)
 
     def sync_all():
         if world > 1:
