@@ -273,6 +273,7 @@ class CrossSS2D(nn.Module):
         self.d_inner = int(ssm_ratio * d_model)
         self.dt_rank = math.ceil(d_model / 16)
         self.in_proj = nn.Linear(d_model, self.d_inner * 2, bias=False)      # present in the reference, never used (:399)
+        self.in_proj.weight.requires_grad_(False)   # it never receives a gradient there either; frozen so DDP does not wait for it
         self.in_proj_sec = nn.Linear(d_model, self.d_inner, bias=False)
         self.conv2d = nn.Conv2d(self.d_inner, self.d_inner, 3, padding=1, groups=self.d_inner, bias=True)
         self.x_proj_weight = nn.Parameter(torch.empty(4, self.dt_rank + 2 * d_state, self.d_inner).uniform_(-1, 1) * self.d_inner ** -0.5)
@@ -331,6 +332,11 @@ class TwoViewXFMamba(nn.Module):
         if backbone is not None:
             cfg.update(backbone)
         self.mamba_feature_extrac = Backbone(**cfg)
+        # only the last stage's feature map is consumed (net_fusionmamba.py:200-201): outnorm0..2 never receive a gradient
+        # in the reference either; frozen so DDP does not wait for them
+        for i in range(len(self.mamba_feature_extrac.dims) - 1):
+            for p_ in getattr(self.mamba_feature_extrac, f"outnorm{i}").parameters():
+                p_.requires_grad_(False)
         self.shallow_mamba_fusion = ShallowFusionBlock(hidden, d_state)
         self.fusemamba = DeepFusion(hidden, 1, (0.0,), d_state)
         self.final_conv = nn.Conv2d(hidden, hidden, 1)
