@@ -14,6 +14,9 @@ int launch_scan_bwd(const xfs_scan_bwd_args&, cudaStream_t);
 int launch_ss2d_fwd(const xfs_ss2d_fwd_args&, cudaStream_t);
 int launch_ss2d_bwd(const xfs_ss2d_bwd_args&, cudaStream_t);
 int ss2d_supported(int64_t, int64_t, int64_t, int64_t, int, int);
+int ss2d_small_supported(int64_t, int64_t, int64_t);
+int launch_ss2d_small_fwd(const xfs_ss2d_fwd_args&, cudaStream_t);
+int launch_ss2d_small_bwd(const xfs_ss2d_bwd_args&, cudaStream_t);
 
 static std::atomic<long long> g_launches{0};
 
@@ -118,7 +121,7 @@ int xfs_selective_scan_bwd(const xfs_scan_bwd_args* a, xfs_stream_t stream) {
 
 int xfs_ss2d_supported(int64_t D, int64_t N, int64_t H, int64_t W, int dtype, int backward) {
     if (D <= 0 || N <= 0 || H <= 0 || W <= 0 || bad_dtype(dtype)) return 0;
-    return ss2d_supported(D, N, H, W, dtype, backward);
+    return ss2d_small_supported(N, H, W) || ss2d_supported(D, N, H, W, dtype, backward);
 }
 
 int xfs_ss2d_fwd(const xfs_ss2d_fwd_args* a, xfs_stream_t stream) {
@@ -126,6 +129,7 @@ int xfs_ss2d_fwd(const xfs_ss2d_fwd_args* a, xfs_stream_t stream) {
     if (a->batch <= 0 || a->D <= 0 || a->N <= 0 || a->H <= 0 || a->W <= 0) return XFS_ERR_SHAPE;
     if (bad_dtype(a->dtype) || (a->out_dtype != XFS_F32 && a->out_dtype != a->dtype)) return XFS_ERR_DTYPE;
     if (a->scans != XFS_SCANS_CROSS2D) return XFS_ERR_UNSUPPORTED;
+    if (ss2d_small_supported(a->N, a->H, a->W)) return launch_ss2d_small_fwd(*a, (cudaStream_t)stream);   // L <= 64
     if (!ss2d_supported(a->D, a->N, a->H, a->W, a->dtype, 0)) return XFS_ERR_UNSUPPORTED;
     return launch_ss2d_fwd(*a, (cudaStream_t)stream);
 }
@@ -138,6 +142,7 @@ int xfs_ss2d_bwd(const xfs_ss2d_bwd_args* a, xfs_stream_t stream) {
     if (a->batch <= 0 || a->D <= 0 || a->N <= 0 || a->H <= 0 || a->W <= 0) return XFS_ERR_SHAPE;
     if (bad_dtype(a->dtype) || (a->dout_dtype != XFS_F32 && a->dout_dtype != a->dtype)) return XFS_ERR_DTYPE;
     if (a->scans != XFS_SCANS_CROSS2D) return XFS_ERR_UNSUPPORTED;
+    if (ss2d_small_supported(a->N, a->H, a->W)) return launch_ss2d_small_bwd(*a, (cudaStream_t)stream);   // L <= 64
     if (!ss2d_supported(a->D, a->N, a->H, a->W, a->dtype, 1)) return XFS_ERR_UNSUPPORTED;
     return launch_ss2d_bwd(*a, (cudaStream_t)stream);
 }

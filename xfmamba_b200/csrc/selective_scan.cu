@@ -233,7 +233,12 @@ static int launch_fwd_t(const xfs_scan_fwd_args& a, cudaStream_t st) {
     return check_launch();
 }
 
+int launch_scan_small_fwd(const xfs_scan_fwd_args& a, cudaStream_t st);
+int launch_scan_small_bwd(const xfs_scan_bwd_args& a, cudaStream_t st);
+bool scan_small_supported(int64_t L, int64_t N);
+
 int launch_scan_fwd(const xfs_scan_fwd_args& a, cudaStream_t st) {
+    if (scan_small_supported(a.seqlen, a.dstate)) return launch_scan_small_fwd(a, st);
     switch (a.dtype) {
         case XFS_F32: return launch_fwd_t<float>(a, st);
         case XFS_BF16: return launch_fwd_t<__nv_bfloat16>(a, st);
@@ -253,11 +258,238 @@ static int launch_bwd_t(const xfs_scan_bwd_args& a, cudaStream_t st) {
 }
 
 int launch_scan_bwd(const xfs_scan_bwd_args& a, cudaStream_t st) {
+    if (scan_small_supported(a.seqlen, a.dstate)) return launch_scan_small_bwd(a, st);
     switch (a.dtype) {
         case XFS_F32: return launch_bwd_t<float>(a, st);
         case XFS_BF16: return launch_bwd_t<__nv_bfloat16>(a, st);
         default: return launch_bwd_t<__half>(a, st);
     }
 }
+
+}  // namespace xfs
+
+// =========================================================================================================
+// short sequences (L <= 64, N <= 16): XFMamba's shallow-fusion scan (K = 2 groups, N = 16, L = 49, dim = 2 x 1536/2048;
+// reference models/fusion_vmamba.py:831-833).  One sequence per 8-lane group, 16 rows per CTA step; in the backward a
+// CTA walks up to 128 rows of ONE (batch, group) and sums their dB/dC in shared memory before a single atomic per
+// (n, l) leaves the CTA -- the general kernel above (and the reference) pay one atomic per row.
+// =========================================================================================================
+#include "ss2d_fused.cuh"
+
+namespace xfs {
+
+constexpr int kRowsPerStep = 16;     // 4 warps x 4 lane groups
+constexpr int kRowSteps = 8;         // backward: steps per CTA -> 128 rows
+
+template <typename T, typename TO>
+__global__ void __launch_bounds__(128)
+sscan_small_fwd_kernel(const xfs_scan_fwd_args p) {
+    const int lane = threadIdx.x & 31, g = lane >> 3, j = lane & 7;
+    const int64_t row = (int64_t)blockIdx.x * kRowsPerStep + (threadIdx.x >> 5) * 4 + g;      // b*dim + d
+    const bool valid = row < p.batch * p.dim;
+    const int64_t r = valid ? row : 0;
+    const int L = (int)p.seqlen, N = (int)p.dstate;
+    const int64_t b = r / p.dim, d = r % p.dim, grp = d / (p.dim / p.ngroups);
+    const T* __restrict__ Bg = reinterpret_cast<const T*>(p.B) + (b * p.ngroups + grp) * N * L;
+    const T* __restrict__ Cg = reinterpret_cast<const T*>(p.C) + (b * p.ngroups + grp) * N * L;
+    const bool vin = row_vec_ok(reinterpret_cast<const T*>(p.u), L) && row_vec_ok(reinterpret_cast<const T*>(p.delta), L) &&
+                     row_vec_ok(reinterpret_cast<const T*>(p.B), L) && row_vec_ok(reinterpret_cast<const T*>(p.C), L);
+    const bool vout = row_vec_ok(reinterpret_cast<const TO*>(p.out), L);
+    const float bias = p.delta_bias ? p.delta_bias[d] : 0.0f;
+    const float Dd = p.D ? p.D[d] : 0.0f;
+    const int l0 = j * 8;
+    float dt[8], u[8], y[8];
+    load8<T, true>(reinterpret_cast<const T*>(p.delta) + r * L, l0, L, vin, dt);
+    load8<T, true>(reinterpret_cast<const T*>(p.u) + r * L, l0, L, vin, u);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float xx = dt[i] + bias;
+        float e;
+        const float sp = p.delta_softplus ? softplus_fwd(xx, e) : xx;
+        const bool in = l0 + i < L;
+        dt[i] = in ? sp : 0.0f;
+        u[i] = in ? u[i] : 0.0f;
+        y[i] = Dd * u[i];
+    }
+    for (int n = 0; n < N; ++n) {
+        float Bv[8], Cv[8], S[8], P[8];
+        load8<T, true>(Bg + n * L, l0, L, vin, Bv);
+        load8<T, true>(Cg + n * L, l0, L, vin, Cv);
+        const float A2 = p.A[d * N + n] * kLog2e;
+        float Pr = 1.0f, Sr = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float a = ex2(dt[i] * A2);
+            Sr = fmaf(a, Sr, (dt[i] * Bv[i]) * u[i]);
+            Pr *= a;
+            S[i] = Sr; P[i] = Pr;
+        }
+        float h_end;
+        const float h_in = group_prefix<false>(Pr, Sr, j, h_end);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = fmaf(Cv[i], fmaf(P[i], h_in, S[i]), y[i]);
+        if (p.states && valid && j == 0) p.states[r * N + n] = h_end;
+    }
+    if (valid) store8<TO>(reinterpret_cast<TO*>(p.out) + r * L, l0, L, vout, y);
+}
+
+template <typename T, typename TDO>
+__global__ void __launch_bounds__(128)
+sscan_small_bwd_kernel(const xfs_scan_bwd_args p) {
+    extern __shared__ __align__(16) float sm[];
+    const int L = (int)p.seqlen, N = (int)p.dstate;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 3, j = lane & 7;
+    float* mydB = sm + w * N * kSmallL;                 // [4 warps][N][64]
+    float* mydC = sm + (4 + w) * N * kSmallL;
+    for (int i = threadIdx.x; i < 8 * N * kSmallL; i += 128) sm[i] = 0.0f;
+    __syncthreads();
+
+    const int64_t Dg = p.dim / p.ngroups;
+    const int64_t nblk = (Dg + kRowsPerStep * kRowSteps - 1) / (kRowsPerStep * kRowSteps);
+    const int64_t bg = blockIdx.x / nblk;               // b*ngroups + grp
+    const int64_t blk = blockIdx.x - bg * nblk;
+    const int64_t b = bg / p.ngroups, grp = bg % p.ngroups;
+    const T* __restrict__ Bg = reinterpret_cast<const T*>(p.B) + bg * N * L;
+    const T* __restrict__ Cg = reinterpret_cast<const T*>(p.C) + bg * N * L;
+    const bool vin = row_vec_ok(reinterpret_cast<const T*>(p.u), L) && row_vec_ok(reinterpret_cast<const T*>(p.delta), L) &&
+                     row_vec_ok(reinterpret_cast<const T*>(p.B), L) && row_vec_ok(reinterpret_cast<const T*>(p.C), L);
+    const bool vdy = row_vec_ok(reinterpret_cast<const TDO*>(p.dout), L);
+    const bool vout = row_vec_ok(reinterpret_cast<const T*>(p.du), L) && row_vec_ok(reinterpret_cast<const T*>(p.ddelta), L);
+    const int l0 = j * 8;
+
+    for (int it = 0; it < kRowSteps; ++it) {
+        const int64_t dg = blk * kRowsPerStep * kRowSteps + it * kRowsPerStep + w * 4 + g;      // channel inside the group
+        const bool valid = dg < Dg;
+        const int64_t d = grp * Dg + (valid ? dg : 0);
+        const int64_t r = b * p.dim + d;
+        const float bias = p.delta_bias ? p.delta_bias[d] : 0.0f;
+        const float Dd = p.D ? p.D[d] : 0.0f;
+        float dt[8], u[8], dy[8], sig[8], du[8], ddt[8];
+        load8<T, true>(reinterpret_cast<const T*>(p.delta) + r * L, l0, L, vin, dt);
+        load8<T, true>(reinterpret_cast<const T*>(p.u) + r * L, l0, L, vin, u);
+        load8<TDO, true>(reinterpret_cast<const TDO*>(p.dout) + r * L, l0, L, vdy, dy);
+        float dD_acc = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float xx = dt[i] + bias;
+            float e = 0.0f;
+            const float sp = p.delta_softplus ? softplus_fwd(xx, e) : xx;
+            sig[i] = p.delta_softplus ? ((xx > 20.0f) ? 1.0f : e * rcp(1.0f + e)) : 1.0f;
+            const bool in = (l0 + i < L) && valid;
+            dt[i] = in ? sp : 0.0f;
+            u[i] = in ? u[i] : 0.0f;
+            dy[i] = in ? dy[i] : 0.0f;
+            du[i] = Dd * dy[i];
+            ddt[i] = 0.0f;
+            dD_acc = fmaf(dy[i], u[i], dD_acc);
+        }
+        for (int n = 0; n < N; ++n) {
+            float Bv[8], Cv[8], a[8], bu[8], S[8], P[8], Sq[8], Pq[8];
+            load8<T, true>(Bg + n * L, l0, L, vin, Bv);
+            load8<T, true>(Cg + n * L, l0, L, vin, Cv);
+            const float An = p.A[d * N + n];
+            const float A2 = An * kLog2e;
+            float Pr = 1.0f, Sr = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                a[i] = ex2(dt[i] * A2);
+                bu[i] = (dt[i] * Bv[i]) * u[i];
+                Sr = fmaf(a[i], Sr, bu[i]); Pr *= a[i]; S[i] = Sr; P[i] = Pr;
+            }
+            float unused;
+            const float h_in = group_prefix<false>(Pr, Sr, j, unused);
+            Pr = 1.0f; Sr = 0.0f;
+#pragma unroll
+            for (int i = 7; i >= 0; --i) { Sr = a[i] * fmaf(Cv[i], dy[i], Sr); Pr *= a[i]; Sq[i] = Sr; Pq[i] = Pr; }
+            const float q_in = group_prefix<true>(Pr, Sr, j, unused);
+            float dA_part = 0.0f, dBv[8], dCv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float h = fmaf(P[i], h_in, S[i]);
+                const float q_next = (i == 7) ? q_in : fmaf(Pq[i == 7 ? 7 : i + 1], q_in, Sq[i == 7 ? 7 : i + 1]);
+                const float gi = fmaf(Cv[i], dy[i], q_next);
+                const float hp = h - bu[i];
+                const float gdt = gi * dt[i];
+                du[i] = fmaf(gdt, Bv[i], du[i]);
+                ddt[i] = fmaf(gi, fmaf(Bv[i], u[i], An * hp), ddt[i]);
+                dA_part = fmaf(gdt, hp, dA_part);
+                dBv[i] = quad_sum(gdt * u[i]);
+                dCv[i] = quad_sum(dy[i] * h);
+            }
+            if (g == 0) {
+                float* rb = mydB + n * kSmallL + l0;
+                float* rc = mydC + n * kSmallL + l0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { rb[i] += dBv[i]; rc[i] += dCv[i]; }
+            }
+            dA_part = group_sum(dA_part);
+            if (valid && j == 0) atomicAdd(p.dA + d * N + n, dA_part);
+        }
+        float dbias_acc = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { ddt[i] *= sig[i]; dbias_acc += ddt[i]; }
+        dD_acc = group_sum(dD_acc);
+        dbias_acc = group_sum(dbias_acc);
+        if (valid) {
+            if (j == 0) {
+                if (p.dD) atomicAdd(p.dD + d, dD_acc);
+                if (p.ddelta_bias) atomicAdd(p.ddelta_bias + d, dbias_acc);
+            }
+            store8<T>(reinterpret_cast<T*>(p.du) + r * L, l0, L, vout, du);
+            store8<T>(reinterpret_cast<T*>(p.ddelta) + r * L, l0, L, vout, ddt);
+        }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < N * L; idx += 128) {
+        const int n = idx / L, l = idx - n * L;
+        const int o = n * kSmallL + l;
+        const float vb = sm[o] + sm[N * kSmallL + o] + sm[2 * N * kSmallL + o] + sm[3 * N * kSmallL + o];
+        const float vc = sm[4 * N * kSmallL + o] + sm[5 * N * kSmallL + o] + sm[6 * N * kSmallL + o] + sm[7 * N * kSmallL + o];
+        atomicAdd(p.dB + bg * N * L + idx, vb);
+        atomicAdd(p.dC + bg * N * L + idx, vc);
+    }
+}
+
+static bool small_ok(int64_t L, int64_t N) { return L <= kSmallL && N <= kSmallMaxN; }
+
+template <typename T>
+static int launch_small_fwd(const xfs_scan_fwd_args& a, cudaStream_t st) {
+    const unsigned grid = (unsigned)((a.batch * a.dim + kRowsPerStep - 1) / kRowsPerStep);
+    if (a.out_dtype == XFS_F32) sscan_small_fwd_kernel<T, float><<<grid, 128, 0, st>>>(a);
+    else sscan_small_fwd_kernel<T, T><<<grid, 128, 0, st>>>(a);
+    return check_launch();
+}
+
+template <typename T>
+static int launch_small_bwd(const xfs_scan_bwd_args& a, cudaStream_t st) {
+    const int64_t Dg = a.dim / a.ngroups;
+    const int64_t nblk = (Dg + kRowsPerStep * kRowSteps - 1) / (kRowsPerStep * kRowSteps);
+    const unsigned grid = (unsigned)(a.batch * a.ngroups * nblk);
+    const size_t smem = sizeof(float) * (size_t)(8 * a.dstate * kSmallL);
+    if (a.dout_dtype == XFS_F32) {
+        if (int rc = set_smem(sscan_small_bwd_kernel<T, float>, smem)) return rc;
+        sscan_small_bwd_kernel<T, float><<<grid, 128, smem, st>>>(a);
+    } else {
+        if (int rc = set_smem(sscan_small_bwd_kernel<T, T>, smem)) return rc;
+        sscan_small_bwd_kernel<T, T><<<grid, 128, smem, st>>>(a);
+    }
+    return check_launch();
+}
+
+int launch_scan_small_fwd(const xfs_scan_fwd_args& a, cudaStream_t st) {
+    switch (a.dtype) {
+        case XFS_F32: return launch_small_fwd<float>(a, st);
+        case XFS_BF16: return launch_small_fwd<__nv_bfloat16>(a, st);
+        default: return launch_small_fwd<__half>(a, st);
+    }
+}
+int launch_scan_small_bwd(const xfs_scan_bwd_args& a, cudaStream_t st) {
+    switch (a.dtype) {
+        case XFS_F32: return launch_small_bwd<float>(a, st);
+        case XFS_BF16: return launch_small_bwd<__nv_bfloat16>(a, st);
+        default: return launch_small_bwd<__half>(a, st);
+    }
+}
+bool scan_small_supported(int64_t L, int64_t N) { return small_ok(L, N); }
 
 }  // namespace xfs

@@ -71,6 +71,39 @@ __device__ __forceinline__ void row_store8(T* __restrict__ row, int l0, int L, b
     else store8<T>(row, l0, L, vec_ok, v);
 }
 
+// ---- short sequences (L <= 64): one sequence per 8-lane group, see ss2d_small.cu ---------------------------------
+constexpr int kSmallL = 64;          // positions per sequence slot
+constexpr int kSmallMaxN = 16;
+constexpr int kQuad = 4;             // channels per warp (one per 8-lane group)
+constexpr int kQuadsPerCta = 8;      // backward: quads walked by one CTA
+
+// inclusive scan of affine maps over the 8 lanes of a group; returns the state ENTERING this lane (sequence starts at 0)
+template <bool kRev>
+__device__ __forceinline__ float group_prefix(float P, float S, int j, float& seq_out) {
+#pragma unroll
+    for (int off = 1; off < 8; off <<= 1) {
+        const float Pn = kRev ? __shfl_down_sync(kFull, P, off, 8) : __shfl_up_sync(kFull, P, off, 8);
+        const float Sn = kRev ? __shfl_down_sync(kFull, S, off, 8) : __shfl_up_sync(kFull, S, off, 8);
+        const bool has = kRev ? (j + off < 8) : (j >= off);
+        if (has) { S = fmaf(P, Sn, S); P = P * Pn; }
+    }
+    seq_out = __shfl_sync(kFull, S, kRev ? 0 : 7, 8);          // state after the whole sequence (carry-in is 0)
+    const float prev = kRev ? __shfl_down_sync(kFull, S, 1, 8) : __shfl_up_sync(kFull, S, 1, 8);
+    const bool first = kRev ? (j == 7) : (j == 0);
+    return first ? 0.0f : prev;
+}
+
+__device__ __forceinline__ float group_sum(float v) {            // sum over the 8 lanes of a group
+#pragma unroll
+    for (int off = 4; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off, 8);
+    return v;
+}
+__device__ __forceinline__ float quad_sum(float v) {             // sum over the 4 groups of a warp (same j)
+    v += __shfl_xor_sync(kFull, v, 8);
+    v += __shfl_xor_sync(kFull, v, 16);
+    return v;
+}
+
 inline size_t fwd_smem(int64_t L, int64_t N, int ch) {
     return sizeof(float) * (size_t)(4 * ch * buf_len(L) + (N == 1 ? 0 : 4 * ch * kFusedMaxState));
 }
