@@ -53,6 +53,7 @@ def main():
     ap.add_argument("--so", default=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "xfmamba_b200", "libxfscan.so"))
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--sass", action="store_true", help="also list the hottest SASS instructions")
+    ap.add_argument("--op", default=None, help="only count SASS instructions whose opcode matches this regex (e.g. 'IMAD.MOV|^MOV')")
     a = ap.parse_args()
 
     raw = subprocess.run(["ncu", "-i", a.report, "--page", "source", "--csv", "--kernel-name", f"regex:{a.kernel}"],
@@ -85,6 +86,10 @@ def main():
         loc, _ = mp.get(off, ((("?", 0, "")), ""))
         inst = float(r[ix["Instructions Executed"]] or 0)
         samp = float(r[ix["# Samples"]] or 0)
+        if a.op:
+            toks = [t for t in r[ix["Source"]].split() if not t.startswith("@")]
+            if not toks or not re.search(a.op, toks[0]):
+                continue
         key = (loc[0], loc[1])
         per_line[key][0] += inst
         per_line[key][1] += samp
@@ -97,7 +102,7 @@ def main():
         sass_rows.append((samp, inst, off, r[ix["Source"]].strip(), key))
     print(f"# total warp instructions {tot_i:.3e}, stall samples {tot_s:.0f}")
     srcs = {}
-    for (f, l), (inst, samp, st) in sorted(per_line.items(), key=lambda kv: -kv[1][1])[: a.top]:
+    for (f, l), (inst, samp, st) in sorted(per_line.items(), key=lambda kv: -(kv[1][0] if a.op else kv[1][1]))[: a.top]:
         if f not in srcs:
             p = os.path.join(os.path.dirname(a.so), "csrc", f)
             srcs[f] = open(p).read().splitlines() if os.path.exists(p) else []

@@ -100,8 +100,8 @@ ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
             }
         };
 
-        BwdChunk<kN, kCh> cur, nxt;
-        load_chunk(0, cur);             // in flight while the images are staged
+        BwdChunk<kN, kCh> c;            // ONE register set: re-loaded for the next chunk as soon as this one is consumed
+        load_chunk(0, c);               // in flight while the images are staged
         {
             const T* __restrict__ x = reinterpret_cast<const T*>(p.x);
             const TDO* __restrict__ dyp = reinterpret_cast<const TDO*>(p.dy);
@@ -115,10 +115,12 @@ ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
                 for (int i = tid; i < 2 * 4 * kCh * kFusedMaxState; i += 128) s_q[i] = 0.0f;
             cta_barrier();
         }
+        f2 dD2[kCh], dbias2[kCh], dA2[kCh];
+#pragma unroll
+        for (int ch = 0; ch < kCh; ++ch) { dD2[ch] = splat2(0.0f); dbias2[ch] = splat2(0.0f); dA2[ch] = splat2(0.0f); }
 
 #pragma unroll 1
         for (int step = 0; step < nch; ++step) {
-            BwdChunk<kN, kCh>& c = cur;
             const int j = rev ? step : (nch - 1 - step);
             const int p0 = j * kChunk + lane * kItems;
             const int l0 = rev ? L - 8 - p0 : p0;
@@ -127,121 +129,157 @@ ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
             const bool in_buf = p0 < Lb;
             const bool tail = p0 + 8 > L;
 
-            // ---- read every load register once, then issue the next chunk's loads (scoreboard note in the header)
-            float xraw[kCh][8], Bv[8], Cv[8], hst[kCh];
+            // ---- consume every load register (dt -> dt + bias, B -> copy and B*u, C -> C*dy), then re-load the SAME
+            // registers with the next chunk: the loads fly during the whole computation below and nothing below waits on
+            // a load scoreboard (see ss2d_fused.cuh)
+            f2 x2[kCh][4], u2[kCh][4], dy2[kCh][4], B2[4], Bu2[kCh][4], Cdy2[kCh][4];
+            float hst[kCh];
 #pragma unroll
             for (int ch = 0; ch < kCh; ++ch) {
-                float dtp[8];
-                to_pos<rev>(c.dt[ch], dtp);
+                float u[8], dy[8], dtp[8];
+                if (in_buf) { lds8(xb + ch * Lb, f4s, u); lds8(gb + ch * Lb, f4s, dy); }
+                else {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) xraw[ch][i] = dtp[i] + bias[ch];
+                    for (int i = 0; i < 8; ++i) { u[i] = 0.0f; dy[i] = 0.0f; }
+                }
+                pack8(u, u2[ch]); pack8(dy, dy2[ch]);
+                to_pos<rev>(c.dt[ch], dtp);
+                pack8(dtp, x2[ch]);
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) x2[ch][jj] = add2(x2[ch][jj], splat2(bias[ch]));
                 hst[ch] = (kN == 1) ? c.hstart[ch] + rt_zero : 0.0f;
             }
             if (kN == 1) {
                 float Bp[8], Cp[8];
+                f2 C2[4];
                 to_pos<rev>(c.B, Bp); to_pos<rev>(c.C, Cp);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { Bv[i] = Bp[i] + rt_zero; Cv[i] = Cp[i] + rt_zero; }
-            }
-            if (step + 1 < nch) load_chunk(step + 1, nxt);
-
-            float dt[kCh][8], u[kCh][8], dy[kCh][8], sig[kCh][8], du[kCh][8], ddt[kCh][8];
-#pragma unroll
-            for (int ch = 0; ch < kCh; ++ch) {
-                if (in_buf) { lds8(xb + ch * Lb, f4s, u[ch]); lds8(gb + ch * Lb, f4s, dy[ch]); }
-                else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) { u[ch][i] = 0.0f; dy[ch][i] = 0.0f; }
-                }
+                pack8(Bp, B2); pack8(Cp, C2);
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
-                    const f2 xx = make_float2(xraw[ch][2 * jj], xraw[ch][2 * jj + 1]);
-                    f2 e = splat2(0.0f);
-                    const f2 sp = p.delta_softplus ? softplus2(xx, e) : xx;
-                    dt[ch][2 * jj] = sp.x; dt[ch][2 * jj + 1] = sp.y;
-                    // sigmoid(x) = e / (1 + e); x > 20 -> 1 (softplus is the identity there)
-                    sig[ch][2 * jj] = p.delta_softplus ? ((xx.x > 20.0f) ? 1.0f : e.x * rcp(1.0f + e.x)) : 1.0f;
-                    sig[ch][2 * jj + 1] = p.delta_softplus ? ((xx.y > 20.0f) ? 1.0f : e.y * rcp(1.0f + e.y)) : 1.0f;
-                }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (tail && p0 + i >= L) dt[ch][i] = 0.0f;
-                    du[ch][i] = Dd[ch] * dy[ch][i];
-                    ddt[ch][i] = 0.0f;
-                    dD_acc[ch] = fmaf(dy[ch][i], u[ch][i], dD_acc[ch]);
+                    for (int ch = 0; ch < kCh; ++ch) {
+                        Bu2[ch][jj] = mul2(B2[jj], u2[ch][jj]);
+                        Cdy2[ch][jj] = mul2(C2[jj], dy2[ch][jj]);
+                    }
+                    B2[jj] = add2(B2[jj], splat2(rt_zero));          // private copy: B is needed again for du
+                }
+            }
+            if (step + 1 < nch) load_chunk(step + 1, c);
+
+            f2 dt2[kCh][4], sig2[kCh][4], du2[kCh][4], ddt2[kCh][4];
+#pragma unroll
+            for (int ch = 0; ch < kCh; ++ch) {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const f2 xx = x2[ch][jj];
+                    f2 e = splat2(0.0f);
+                    dt2[ch][jj] = p.delta_softplus ? softplus2(xx, e) : xx;
+                    // sigmoid(x) = e / (1 + e); x > 20 -> 1 (softplus is the identity there)
+                    const f2 w = add2(e, splat2(1.0f));
+                    f2 sg = mul2(e, make_float2(rcp(w.x), rcp(w.y)));
+                    sg.x = (xx.x > 20.0f) ? 1.0f : sg.x;
+                    sg.y = (xx.y > 20.0f) ? 1.0f : sg.y;
+                    sig2[ch][jj] = p.delta_softplus ? sg : splat2(1.0f);
+                    du2[ch][jj] = mul2(splat2(Dd[ch]), dy2[ch][jj]);
+                    ddt2[ch][jj] = splat2(0.0f);
+                    dD2[ch] = fma2(dy2[ch][jj], u2[ch][jj], dD2[ch]);
+                }
+                if (tail) {
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        if (p0 + 2 * jj >= L) dt2[ch][jj].x = 0.0f;
+                        if (p0 + 2 * jj + 1 >= L) dt2[ch][jj].y = 0.0f;
+                    }
                 }
             }
             for (int n = 0; n < N; ++n) {
-                float dBv[8], dCv[8];
+                f2 dB2[4], dC2[4];
                 if (kN != 1) {
-                    float Bl[8], Cl[8];
+                    float Bl[8], Cl[8], Bp[8], Cp[8];
+                    f2 C2[4];
                     row_load8<T, kFast>(Bk + n * L, l0, L, vin, Bl);
                     row_load8<T, kFast>(Ck + n * L, l0, L, vin, Cl);
-                    to_pos<rev>(Bl, Bv); to_pos<rev>(Cl, Cv);
+                    to_pos<rev>(Bl, Bp); to_pos<rev>(Cl, Cp);
+                    pack8(Bp, B2); pack8(Cp, C2);
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                        for (int ch = 0; ch < kCh; ++ch) {
+                            Bu2[ch][jj] = mul2(B2[jj], u2[ch][jj]);
+                            Cdy2[ch][jj] = mul2(C2[jj], dy2[ch][jj]);
+                        }
                 }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { dBv[i] = 0.0f; dCv[i] = 0.0f; }
+                for (int jj = 0; jj < 4; ++jj) { dB2[jj] = splat2(0.0f); dC2[jj] = splat2(0.0f); }
 #pragma unroll
                 for (int ch = 0; ch < kCh; ++ch) {
                     const float An = (kN == 1) ? A_1[ch] : p.A[kd[ch] * N + n];
                     const float A2 = An * kLog2e;
-                    float a[8], bu[8], S[8], P[8], Sq[8], Pq[8];
-                    float Pr = 1.0f, Sr = 0.0f;
+                    f2 a2[4], bu2[4], S2[4], P2[4], Sq2[4], Pq2[4];
+                    float a[8], bu[8], cd[8], S[8], P[8], Sq[8], Pq[8];
                     const float h_start = (kN == 1) ? hst[ch]
                                                     : ((jprev >= 0 && jprev < nch) ? st_row[ch][jprev * N + n] : 0.0f);
-                    float unused, h_in, q_in, q_out;
+                    float unused, q_out;
                     float* qs = s_q + (k * kCh + ch) * kFusedMaxState + n;
                     const float qc = (kN == 1) ? qcarry1[ch] : *qs;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        a[i] = ex2(dt[ch][i] * A2);
-                        bu[i] = (dt[ch][i] * Bv[i]) * u[ch][i];
+                    for (int jj = 0; jj < 4; ++jj) {
+                        a2[jj] = ex2_2(mul2(dt2[ch][jj], splat2(A2)));
+                        bu2[jj] = mul2(dt2[ch][jj], Bu2[ch][jj]);
                     }
-                    if (!rev) {
+                    unpack8(a2, a); unpack8(bu2, bu); unpack8(Cdy2[ch], cd);
+                    // forward re-scan (walk order) and adjoint scan (opposite order): serial folds, scalar
+                    float Pr = 1.0f, Sr = 0.0f;
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) { Sr = fmaf(a[i], Sr, bu[i]); Pr *= a[i]; S[i] = Sr; P[i] = Pr; }
-                        h_in = warp_prefix<false>(Pr, Sr, h_start, lane, unused);
-                        Pr = 1.0f; Sr = 0.0f;
-#pragma unroll
-                        for (int i = 7; i >= 0; --i) { Sr = a[i] * fmaf(Cv[i], dy[ch][i], Sr); Pr *= a[i]; Sq[i] = Sr; Pq[i] = Pr; }
-                        q_in = warp_prefix<true>(Pr, Sr, qc, lane, q_out);
-                    } else {
-#pragma unroll
-                        for (int i = 7; i >= 0; --i) { Sr = fmaf(a[i], Sr, bu[i]); Pr *= a[i]; S[i] = Sr; P[i] = Pr; }
-                        h_in = warp_prefix<true>(Pr, Sr, h_start, lane, unused);
-                        Pr = 1.0f; Sr = 0.0f;
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) { Sr = a[i] * fmaf(Cv[i], dy[ch][i], Sr); Pr *= a[i]; Sq[i] = Sr; Pq[i] = Pr; }
-                        q_in = warp_prefix<false>(Pr, Sr, qc, lane, q_out);
+                    for (int ii = 0; ii < 8; ++ii) {
+                        const int i = rev ? 7 - ii : ii;
+                        Sr = fmaf(a[i], Sr, bu[i]); Pr *= a[i]; S[i] = Sr; P[i] = Pr;
                     }
-                    float dA_part = 0.0f;
+                    const float h_in = warp_prefix<rev>(Pr, Sr, h_start, lane, unused);
+                    Pr = 1.0f; Sr = 0.0f;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float h = fmaf(P[i], h_in, S[i]);
-                        // q of the element that FOLLOWS i in the forward walk
-                        const int inx = rev ? (i == 0 ? 0 : i - 1) : (i == 7 ? 7 : i + 1);
-                        const bool edge = rev ? (i == 0) : (i == 7);
-                        const float q_next = edge ? q_in : fmaf(Pq[inx], q_in, Sq[inx]);
-                        const float gi = fmaf(Cv[i], dy[ch][i], q_next);
-                        const float hp = h - bu[i];
-                        const float gdt = gi * dt[ch][i];
-                        du[ch][i] = fmaf(gdt, Bv[i], du[ch][i]);
-                        ddt[ch][i] = fmaf(gi, fmaf(Bv[i], u[ch][i], An * hp), ddt[ch][i]);
-                        dA_part = fmaf(gdt, hp, dA_part);
+                    for (int ii = 0; ii < 8; ++ii) {
+                        const int i = rev ? ii : 7 - ii;
+                        Sr = a[i] * (cd[i] + Sr); Pr *= a[i]; Sq[i] = Sr; Pq[i] = Pr;
+                    }
+                    const float q_in = warp_prefix<!rev>(Pr, Sr, qc, lane, q_out);
+                    pack8(S, S2); pack8(P, P2); pack8(Sq, Sq2); pack8(Pq, Pq2);
+                    // element-wise part on packed pairs
+                    f2 q2[4], gi2[4];
+                    float q[8], gi[8];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) q2[jj] = fma2(Pq2[jj], splat2(q_in), Sq2[jj]);      // q_i (inclusive)
+                    unpack8(q2, q);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {       // g_i = C_i dy_i + q of the element that FOLLOWS i in the forward walk
+                        const float qn = rev ? (i == 0 ? q_in : q[i == 0 ? 0 : i - 1]) : (i == 7 ? q_in : q[i == 7 ? 7 : i + 1]);
+                        gi[i] = cd[i] + qn;
+                    }
+                    pack8(gi, gi2);
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const f2 h2 = fma2(P2[jj], splat2(h_in), S2[jj]);
+                        const f2 hp2 = fma2(bu2[jj], splat2(-1.0f), h2);                 // a_i * h_{i-1}
+                        const f2 gdt2 = mul2(gi2[jj], dt2[ch][jj]);
+                        du2[ch][jj] = fma2(gdt2, B2[jj], du2[ch][jj]);
+                        ddt2[ch][jj] = fma2(gi2[jj], fma2(splat2(An), hp2, Bu2[ch][jj]), ddt2[ch][jj]);
+                        dA2[ch] = fma2(gdt2, hp2, dA2[ch]);
                         if (kCh == 1 || valid[ch]) {
-                            dBv[i] = fmaf(gdt, u[ch][i], dBv[i]);
-                            dCv[i] = fmaf(dy[ch][i], h, dCv[i]);
+                            dB2[jj] = fma2(gdt2, u2[ch][jj], dB2[jj]);
+                            dC2[jj] = fma2(dy2[ch][jj], h2, dC2[jj]);
                         }
                     }
-                    if (kN == 1) { qcarry1[ch] = q_out; dA1[ch] += dA_part; }
+                    if (kN == 1) qcarry1[ch] = q_out;
                     else {
-                        dA_part = warp_sum(dA_part);
+                        float dA_part = warp_sum(dA2[ch].x + dA2[ch].y);
+                        dA2[ch] = splat2(0.0f);
                         __syncwarp();
                         if (lane == 0) { *qs = q_out; s_dA[(k * kCh + ch) * kFusedMaxState + n] += dA_part; }
                     }
                 }
                 // dB / dC of this route at scan positions l0..l0+7 (ascending address order)
-                float dBa[8], dCa[8];
+                float dBv[8], dCv[8], dBa[8], dCa[8];
+                unpack8(dB2, dBv); unpack8(dC2, dCv);
                 to_pos<rev>(dBv, dBa); to_pos<rev>(dCv, dCa);
                 float* dBrow = dBk + n * L;
                 float* dCrow = dCk + n * L;
@@ -270,14 +308,16 @@ ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
             if (!first_touch && !synced) { pair_barrier(k & 1); synced = true; }
 #pragma unroll
             for (int ch = 0; ch < kCh; ++ch) {
+                float ddt[8], du[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    ddt[ch][i] *= sig[ch][i];
-                    dbias_acc[ch] += ddt[ch][i];            // dt = 0 beyond L makes these terms exactly 0
+                for (int jj = 0; jj < 4; ++jj) {
+                    ddt2[ch][jj] = mul2(ddt2[ch][jj], sig2[ch][jj]);
+                    dbias2[ch] = add2(dbias2[ch], ddt2[ch][jj]);       // dt = 0 beyond L makes these terms exactly 0
                 }
+                unpack8(ddt2[ch], ddt); unpack8(du2[ch], du);
                 if (kCh == 1 || valid[ch]) {
                     float dda[8];
-                    to_pos<rev>(ddt[ch], dda);
+                    to_pos<rev>(ddt, dda);
                     row_store8<T, kFast>(ddt_row[ch], l0, L, vout, dda);
                 }
                 if (in_buf) {
@@ -285,12 +325,17 @@ ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
                         float o[8];
                         lds8(db + ch * Lb, f4s, o);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) du[ch][i] += o[i];
+                        for (int i = 0; i < 8; ++i) du[i] += o[i];
                     }
-                    sts8(db + ch * Lb, f4s, du[ch]);
+                    sts8(db + ch * Lb, f4s, du);
                 }
             }
-            cur = nxt;      // register copy (waits for the loads issued a whole chunk ago)
+        }
+#pragma unroll
+        for (int ch = 0; ch < kCh; ++ch) {
+            dD_acc[ch] = dD2[ch].x + dD2[ch].y;
+            dbias_acc[ch] = dbias2[ch].x + dbias2[ch].y;
+            dA1[ch] = dA2[ch].x + dA2[ch].y;
         }
     };  // walk
     if (k >= 2) walk(std::true_type{}); else walk(std::false_type{});

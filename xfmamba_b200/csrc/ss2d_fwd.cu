@@ -77,8 +77,8 @@ ss2d_fwd_kernel(const xfs_ss2d_fwd_args p) {
             }
         };
 
-        FwdChunk<kN, kCh> ca, cb;
-        load_chunk(0, ca);              // in flight while the image is staged
+        FwdChunk<kN, kCh> c0;           // ONE register set: re-loaded for the next chunk as soon as this one is consumed
+        load_chunk(0, c0);              // in flight while the image is staged
         {
             const T* __restrict__ x = reinterpret_cast<const T*>(p.x);
 #pragma unroll
@@ -98,7 +98,8 @@ ss2d_fwd_kernel(const xfs_ss2d_fwd_args p) {
             const bool in_buf = p0 < Lb;                    // lane has shared-memory backing
             const bool tail = p0 + 8 > L;
 
-            // ---- read every load register once, then issue the next chunk's loads (scoreboard note in the header)
+            // ---- read every load register once (dt -> dt + bias, B -> B*u, C -> C + 0), then re-load the SAME registers
+            // with the next chunk: the loads fly during the whole computation below (scoreboard note in the header)
             f2 dt2[kCh][4], u2[kCh][4], y2[kCh][4], Bu2[kCh][4], C1[4];
 #pragma unroll
             for (int ch = 0; ch < kCh; ++ch) {
@@ -220,11 +221,8 @@ ss2d_fwd_kernel(const xfs_ss2d_fwd_args p) {
         };
 
 #pragma unroll 1
-        for (int step = 0; step < nch; step += 2) {
-            compute_chunk(step, ca, [&]() __attribute__((always_inline)) { if (step + 1 < nch) load_chunk(step + 1, cb); });
-            if (step + 1 < nch)
-                compute_chunk(step + 1, cb, [&]() __attribute__((always_inline)) { if (step + 2 < nch) load_chunk(step + 2, ca); });
-        }
+        for (int step = 0; step < nch; ++step)
+            compute_chunk(step, c0, [&]() __attribute__((always_inline)) { if (step + 1 < nch) load_chunk(step + 1, c0); });
     };  // walk
     if (k >= 2) walk(std::true_type{}); else walk(std::false_type{});
     if (!synced) pair_barrier(k & 1);
