@@ -88,7 +88,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.005)
 
     def stop(self):
         self._stop_evt.set()
@@ -187,7 +187,11 @@ def run_ours(args):
     grads = (torch.empty_like(d["x"]), torch.empty_like(d["delta"]), torch.empty_like(d["A"]),
              torch.empty(d["Bs"].shape, dtype=torch.float32, device=dev), torch.empty(d["Cs"].shape, dtype=torch.float32, device=dev),
              torch.empty_like(d["Ds"]), torch.empty_like(d["delta_bias"]))
-    bucket = FlatBucket([grads[2], grads[5], grads[6]])      # dA, dDs, ddelta_bias: the parameter gradients
+    # dA, dDs, ddelta_bias are the parameter gradients.  Two buckets alternate so that the all-reduce of step i (NCCL's own
+    # stream) overlaps the kernels of step i+1, as a gradient bucket does with the rest of a backward pass.
+    buckets = [FlatBucket([grads[2], grads[5], grads[6]]) for _ in range(2)]
+    pending = [None, None]
+    step_no = [0]
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     fwd_ev, bwd_ev = [], []
@@ -210,10 +214,18 @@ def run_ours(args):
             fwd_ev.append((e0, e1))
             bwd_ev.append((e1b, e2))
         if world > 1:   # data-parallel exchange of the parameter gradients (training step): one NCCL all-reduce
-            bucket.pack([grads[2], grads[5], grads[6]])
-            bucket.allreduce(average=True)
+            i = step_no[0] & 1
+            step_no[0] += 1
+            if pending[i] is not None:
+                pending[i].wait()                      # the bucket's previous reduction (two steps ago) must be done
+            buckets[i].pack([grads[2], grads[5], grads[6]])
+            pending[i] = dist.all_reduce(buckets[i].flat, async_op=True)
 
     def sync_all():
+        for i in range(2):
+            if pending[i] is not None:
+                pending[i].wait()
+                pending[i] = None
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -228,6 +240,10 @@ def run_ours(args):
     t_start.record()
     for _ in range(args.steps):
         step(True)
+    for i in range(2):                                  # the last reductions belong to the timed steps
+        if pending[i] is not None:
+            pending[i].wait()
+            pending[i] = None
     t_end.record()
     sync_all()
     launches = _lib.launch_count() - before
