@@ -190,6 +190,18 @@ XFS_API int xfs_ss2d_supported(int64_t D, int64_t N, int64_t H, int64_t W, int d
 XFS_API int xfs_ss2d_fwd(const xfs_ss2d_fwd_args* a, xfs_stream_t stream);
 XFS_API int xfs_ss2d_bwd(const xfs_ss2d_bwd_args* a, xfs_stream_t stream);
 
+/* -------------------------------------------------------------------------------------------------------------
+ * LayerNorm2d: LayerNorm over the channel dimension of a channel-first tensor, the consumer of the merged scan output
+ * (reference LayerNorm2d, models/fusion_vmamba.py:52-57; out_norm at :1183-1188).  x, y, dy, dx: (B, C, HW) dtype;
+ * weight, bias: (C) f32 or NULL; mean, rstd: (B, HW) f32 (written by fwd when non-NULL, required by bwd);
+ * dweight, dbias: (C) f32, ACCUMULATED into (caller zero-fills), nullable.
+ * ----------------------------------------------------------------------------------------------------------- */
+XFS_API int xfs_layernorm2d_fwd(const void* x, const float* weight, const float* bias, void* y, float* mean, float* rstd,
+                                int64_t B, int64_t C, int64_t HW, float eps, int dtype, xfs_stream_t stream);
+XFS_API int xfs_layernorm2d_bwd(const void* x, const void* dy, const float* weight, const float* mean, const float* rstd,
+                                void* dx, float* dweight, float* dbias, int64_t B, int64_t C, int64_t HW, int dtype,
+                                xfs_stream_t stream);
+
 /* number of kernels this library has launched since load (process-wide, relaxed atomic): lets bench.py report
  * `gpu_launches` from a count instead of a guess */
 XFS_API int64_t xfs_launch_count(void);

@@ -15,7 +15,7 @@ import numpy as np
 
 __all__ = [
     "build", "lib", "route_table", "cross_scan", "cross_merge", "cross_merge_1b1", "swap_scan", "swap_merge",
-    "selective_scan_fwd", "selective_scan_bwd", "ss2d_fwd", "ss2d_bwd", "bf16_round", "np_cross_scan",
+    "selective_scan_fwd", "selective_scan_bwd", "ss2d_fwd", "ss2d_bwd", "bf16_round", "np_cross_scan", "layernorm2d",
 ]
 
 _HERE = Path(__file__).resolve().parent
@@ -195,6 +195,20 @@ def ss2d_bwd(x, delta, A, Bs, Cs, Ds, delta_bias, dy, delta_softplus=True, real=
 
 
 # ------------------------------------------------------------------------------------------------
+def layernorm2d(x, weight=None, bias=None, eps=1e-5):
+    """LayerNorm2d (models/fusion_vmamba.py:52-57): layer_norm over C of a channel-first (B, C, ...) array, in float64"""
+    x64 = np.asarray(x, dtype=np.float64)
+    mean = x64.mean(axis=1, keepdims=True)
+    var = x64.var(axis=1, keepdims=True)
+    y = (x64 - mean) / np.sqrt(var + eps)
+    shp = (1, -1) + (1,) * (x64.ndim - 2)
+    if weight is not None:
+        y = y * np.asarray(weight, dtype=np.float64).reshape(shp)
+    if bias is not None:
+        y = y + np.asarray(bias, dtype=np.float64).reshape(shp)
+    return y
+
+
 def bf16_round(a: np.ndarray) -> np.ndarray:
     """round-to-nearest-even float32 -> bfloat16 -> float32 (what torch's .to(bfloat16).float() does)."""
     a = np.ascontiguousarray(a, dtype=np.float32)

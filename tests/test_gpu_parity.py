@@ -399,3 +399,29 @@ def test_native_library_was_used(xf):
     before = _lib.launch_count()
     xf.cross_scan_fn(torch.randn(1, 1, 4, 4, device=dev()))
     assert _lib.launch_count() == before + 1
+
+
+# ================================================================================================ LayerNorm2d (consumer)
+@pytest.mark.parametrize("shape", [(2, 192, 56, 56), (3, 16, 7, 7), (1, 2048, 7, 7), (2, 5, 3, 11), (1, 96, 1, 33)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_layernorm2d_matches_reference_layernorm2d(xf, shape, dtype):
+    """reference LayerNorm2d = permute -> F.layer_norm -> permute (models/fusion_vmamba.py:52-57)"""
+    from xfmamba_b200.norm import layer_norm_2d
+    torch.manual_seed(0)
+    B, C, H, W = shape
+    x = (torch.randn(shape, device=dev()) * 2 + 0.5).to(dtype).requires_grad_(True)
+    w = (torch.rand(C, device=dev()) + 0.5).requires_grad_(True)
+    b = torch.randn(C, device=dev()).requires_grad_(True)
+    g = torch.randn(shape, device=dev()).to(dtype)
+    y = layer_norm_2d(x, w, b, 1e-5)
+    y.backward(g)
+    xr = x.detach().float().clone().requires_grad_(True)
+    wr, br = w.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xr.permute(0, 2, 3, 1), (C,), wr, br, 1e-5).permute(0, 3, 1, 2)
+    yr.backward(g.float())
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    assert rel_err(n(y), oracle.layernorm2d(n(x), n(w), n(b), 1e-5)) < tol      # CPU oracle (float64)
+    assert rel_err(n(y), n(yr)) < tol
+    assert rel_err(n(x.grad), n(xr.grad)) < (1e-4 if dtype == torch.float32 else 2e-2)
+    assert rel_err(n(w.grad), n(wr.grad)) < (1e-4 if dtype == torch.float32 else 2e-2)
+    assert rel_err(n(b.grad), n(br.grad)) < (1e-4 if dtype == torch.float32 else 2e-2)

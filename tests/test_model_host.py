@@ -50,6 +50,12 @@ class OracleOps:
                                                           bias.numpy(), softplus, "f32"))
 
     @staticmethod
+    def layer_norm_2d(x, weight=None, bias=None, eps=1e-5):
+        w = None if weight is None else weight.detach().numpy()
+        b = None if bias is None else bias.detach().numpy()
+        return torch.from_numpy(oracle.layernorm2d(x.numpy(), w, b, eps).astype(np.float32))
+
+    @staticmethod
     def swapping_scan(x, x2):
         return torch.from_numpy(oracle.swap_scan(x.numpy(), x2.numpy()))
 
@@ -64,7 +70,7 @@ def test_logits_match_reference_on_cpu_with_oracle_ops(golden, monkeypatch):
     m, sd, g = _mini(golden)
     m.load_state_dict(sd)
     m.eval()
-    for name in ("ss2d_scan", "cross_scan_fn", "selective_scan_fn", "swapping_scan", "swapping_merge"):
+    for name in ("ss2d_scan", "cross_scan_fn", "selective_scan_fn", "swapping_scan", "swapping_merge", "layer_norm_2d"):
         monkeypatch.setattr(M.OPS, name, getattr(OracleOps, name))
     with torch.no_grad():
         logits = m(torch.from_numpy(g["xa"]), torch.from_numpy(g["xb"]))

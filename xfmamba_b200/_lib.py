@@ -53,6 +53,7 @@ SYMBOLS = [
     "xfs_version", "xfs_error_string", "xfs_device_ok", "xfs_chunk_len", "xfs_num_chunks", "xfs_launch_count",
     "xfs_cross_scan", "xfs_cross_merge", "xfs_swap_scan", "xfs_swap_merge", "xfs_swap_stack",
     "xfs_selective_scan_fwd", "xfs_selective_scan_bwd", "xfs_ss2d_supported", "xfs_ss2d_fwd", "xfs_ss2d_bwd",
+    "xfs_layernorm2d_fwd", "xfs_layernorm2d_bwd",
 ]
 
 
@@ -88,6 +89,8 @@ def lib() -> ctypes.CDLL:
     L.xfs_ss2d_supported.argtypes = [c_i64, c_i64, c_i64, c_i64, ctypes.c_int, ctypes.c_int]
     L.xfs_ss2d_fwd.argtypes = [ctypes.POINTER(Ss2dFwdArgs), c_vp]
     L.xfs_ss2d_bwd.argtypes = [ctypes.POINTER(Ss2dBwdArgs), c_vp]
+    L.xfs_layernorm2d_fwd.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, ctypes.c_float, ctypes.c_int, c_vp]
+    L.xfs_layernorm2d_bwd.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, ctypes.c_int, c_vp]
     _lib = L
     return L
 

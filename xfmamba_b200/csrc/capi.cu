@@ -18,6 +18,9 @@ int ss2d_small_supported(int64_t, int64_t, int64_t);
 int launch_ss2d_small_fwd(const xfs_ss2d_fwd_args&, cudaStream_t);
 int launch_ss2d_small_bwd(const xfs_ss2d_bwd_args&, cudaStream_t);
 
+int launch_ln2d_fwd(const void*, const float*, const float*, void*, float*, float*, int64_t, int64_t, int64_t, float, int, cudaStream_t);
+int launch_ln2d_bwd(const void*, const void*, const float*, const float*, const float*, void*, float*, float*, int64_t, int64_t, int64_t, int, cudaStream_t);
+
 static std::atomic<long long> g_launches{0};
 
 int check_launch() {
@@ -145,6 +148,22 @@ int xfs_ss2d_bwd(const xfs_ss2d_bwd_args* a, xfs_stream_t stream) {
     if (ss2d_small_supported(a->N, a->H, a->W)) return launch_ss2d_small_bwd(*a, (cudaStream_t)stream);   // L <= 64
     if (!ss2d_supported(a->D, a->N, a->H, a->W, a->dtype, 1)) return XFS_ERR_UNSUPPORTED;
     return launch_ss2d_bwd(*a, (cudaStream_t)stream);
+}
+
+int xfs_layernorm2d_fwd(const void* x, const float* weight, const float* bias, void* y, float* mean, float* rstd, int64_t B,
+                        int64_t C, int64_t HW, float eps, int dtype, xfs_stream_t stream) {
+    if (!x || !y || ((mean == nullptr) != (rstd == nullptr))) return XFS_ERR_NULL;
+    if (B <= 0 || C <= 0 || HW <= 0) return XFS_ERR_SHAPE;
+    if (bad_dtype(dtype)) return XFS_ERR_DTYPE;
+    return launch_ln2d_fwd(x, weight, bias, y, mean, rstd, B, C, HW, eps, dtype, (cudaStream_t)stream);
+}
+
+int xfs_layernorm2d_bwd(const void* x, const void* dy, const float* weight, const float* mean, const float* rstd, void* dx,
+                        float* dweight, float* dbias, int64_t B, int64_t C, int64_t HW, int dtype, xfs_stream_t stream) {
+    if (!x || !dy || !mean || !rstd || !dx) return XFS_ERR_NULL;
+    if (B <= 0 || C <= 0 || HW <= 0) return XFS_ERR_SHAPE;
+    if (bad_dtype(dtype)) return XFS_ERR_DTYPE;
+    return launch_ln2d_bwd(x, dy, weight, mean, rstd, dx, dweight, dbias, B, C, HW, dtype, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -28,7 +28,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import csm, csms6s, fusion_ops
+from . import csm, csms6s, fusion_ops, norm
 
 OPS = types.SimpleNamespace(
     ss2d_scan=fusion_ops.ss2d_scan,
@@ -36,6 +36,7 @@ OPS = types.SimpleNamespace(
     selective_scan_fn=csms6s.selective_scan_fn,
     swapping_scan=fusion_ops.SwappingScan_multiview.apply,
     swapping_merge=fusion_ops.SwappingMerge_multiview.apply,
+    layer_norm_2d=norm.layer_norm_2d,
 )
 
 VARIANTS = {   # reference net_fusionmamba.py:151-159
@@ -108,8 +109,10 @@ class Linear2d(nn.Linear):
 
 
 class LayerNorm2d(nn.LayerNorm):
+    """LayerNorm over C of a channel-first tensor (reference :52-57), without the permute/copy round trip"""
+
     def forward(self, x):
-        return F.layer_norm(x.permute(0, 2, 3, 1), self.normalized_shape, self.weight, self.bias, self.eps).permute(0, 3, 1, 2)
+        return OPS.layer_norm_2d(x, self.weight, self.bias, self.eps)
 
 
 class DropPath(nn.Module):
