@@ -26,10 +26,15 @@ ln2d_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const floa
     const float shift = ok ? Elem<T>::to_f(xb[0]) : 0.0f;
     float s1 = 0.0f, s2 = 0.0f;
     if (ok)
-        for (int c = wp; c < C; c += kLnWarps) {
-            const float v = Elem<T>::to_f(xb[(int64_t)c * HW]) - shift;
-            s1 += v;
-            s2 = fmaf(v, v, s2);
+        for (int c0 = wp; c0 < C; c0 += kLnWarps * 4) {
+            float v[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int c = c0 + r * kLnWarps;
+                v[r] = (c < C) ? Elem<T>::to_f(xb[(int64_t)c * HW]) - shift : 0.0f;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { s1 += v[r]; s2 = fmaf(v[r], v[r], s2); }
         }
     s_a[wp][lane] = s1;
     s_b[wp][lane] = s2;
@@ -45,63 +50,102 @@ ln2d_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w, const floa
     if (ok) {
         if (wp == 0 && mean_out) { mean_out[(int64_t)b * HW + pos] = mean; rstd_out[(int64_t)b * HW + pos] = rstd; }
         T* __restrict__ yb = y + (int64_t)b * C * HW + pos;
-        for (int c = wp; c < C; c += kLnWarps) {
-            const float v = (Elem<T>::to_f(xb[(int64_t)c * HW]) - mean) * rstd;
-            yb[(int64_t)c * HW] = Elem<T>::from_f(fmaf(v, w ? w[c] : 1.0f, bias ? bias[c] : 0.0f));
+        for (int c0 = wp; c0 < C; c0 += kLnWarps * 4) {
+            float v[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int c = c0 + r * kLnWarps;
+                v[r] = (c < C) ? Elem<T>::to_f(xb[(int64_t)c * HW]) : 0.0f;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int c = c0 + r * kLnWarps;
+                if (c < C) yb[(int64_t)c * HW] = Elem<T>::from_f(fmaf((v[r] - mean) * rstd, w ? w[c] : 1.0f, bias ? bias[c] : 0.0f));
+            }
         }
     }
 }
+
+constexpr int kLnMaxTilesPerCta = 8;   // backward: a CTA walks up to this many tiles before flushing its dweight/dbias sums
+constexpr int kLnUnroll = 4;           // independent channel rows in flight per warp (the loops are latency bound otherwise)
 
 template <typename T>
 __global__ void __launch_bounds__(kLnWarps * 32)
 ln2d_bwd_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ w, const float* __restrict__ mean_in,
                 const float* __restrict__ rstd_in, T* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, int C,
-                int HW) {
+                int HW, int ntiles_total, int tiles_per_cta) {
+    extern __shared__ float s_acc[];                   // [2][C]: dweight / dbias partial sums of this CTA
     __shared__ float s_a[kLnWarps][kLnPos], s_b[kLnWarps][kLnPos];
     const int tiles = (HW + kLnPos - 1) / kLnPos;
-    const int b = blockIdx.x / tiles, t = blockIdx.x - b * tiles;
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-    const int pos = t * kLnPos + lane;
-    const bool ok = pos < HW;
-    const int64_t base = (int64_t)b * C * HW + pos;
-    const float mean = ok ? mean_in[(int64_t)b * HW + pos] : 0.0f;
-    const float rstd = ok ? rstd_in[(int64_t)b * HW + pos] : 0.0f;
-    float s1 = 0.0f, s2 = 0.0f;
-    for (int c = wp; c < C; c += kLnWarps) {
-        float g = 0.0f, xh = 0.0f;
-        if (ok) {
-            g = Elem<T>::to_f(dy[base + (int64_t)c * HW]);
-            xh = (Elem<T>::to_f(x[base + (int64_t)c * HW]) - mean) * rstd;
-        }
-        const float gw = g * (w ? w[c] : 1.0f);
-        s1 += gw;
-        s2 = fmaf(gw, xh, s2);
-        // parameter gradients: reduce this channel over the 32 positions of the tile
-        float pw = g * xh, pb = g;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            pw += __shfl_xor_sync(kFull, pw, off);
-            pb += __shfl_xor_sync(kFull, pb, off);
-        }
-        if (lane == 0) {
-            if (dw) atomicAdd(dw + c, pw);
-            if (db) atomicAdd(db + c, pb);
-        }
-    }
-    s_a[wp][lane] = s1;
-    s_b[wp][lane] = s2;
+    for (int c = threadIdx.x; c < 2 * C; c += kLnWarps * 32) s_acc[c] = 0.0f;
     __syncthreads();
-    s1 = 0.0f; s2 = 0.0f;
+    const int t_begin = blockIdx.x * tiles_per_cta, t_end = min(t_begin + tiles_per_cta, ntiles_total);
+    for (int gt = t_begin; gt < t_end; ++gt) {
+        const int b = gt / tiles, t = gt - b * tiles;
+        const int pos = t * kLnPos + lane;
+        const bool ok = pos < HW;
+        const int64_t base = (int64_t)b * C * HW + pos;
+        const float mean = ok ? mean_in[(int64_t)b * HW + pos] : 0.0f;
+        const float rstd = ok ? rstd_in[(int64_t)b * HW + pos] : 0.0f;
+        float s1 = 0.0f, s2 = 0.0f;
+        for (int c0 = wp; c0 < C; c0 += kLnWarps * kLnUnroll) {
+            float g[kLnUnroll], xv[kLnUnroll];
 #pragma unroll
-    for (int i = 0; i < kLnWarps; ++i) { s1 += s_a[i][lane]; s2 += s_b[i][lane]; }
-    const float inv = 1.0f / (float)C;
-    s1 *= inv; s2 *= inv;
-    if (ok)
-        for (int c = wp; c < C; c += kLnWarps) {
-            const float g = Elem<T>::to_f(dy[base + (int64_t)c * HW]);
-            const float xh = (Elem<T>::to_f(x[base + (int64_t)c * HW]) - mean) * rstd;
-            dx[base + (int64_t)c * HW] = Elem<T>::from_f(rstd * (g * (w ? w[c] : 1.0f) - s1 - xh * s2));
+            for (int r = 0; r < kLnUnroll; ++r) {           // all loads first
+                const int c = c0 + r * kLnWarps;
+                const bool in = ok && c < C;
+                g[r] = in ? Elem<T>::to_f(dy[base + (int64_t)c * HW]) : 0.0f;
+                xv[r] = in ? Elem<T>::to_f(x[base + (int64_t)c * HW]) : mean;
+            }
+#pragma unroll
+            for (int r = 0; r < kLnUnroll; ++r) {
+                const int c = c0 + r * kLnWarps;
+                const float xh = (xv[r] - mean) * rstd;
+                const float gw = g[r] * ((w && c < C) ? w[c] : 1.0f);
+                s1 += gw;
+                s2 = fmaf(gw, xh, s2);
+                // parameter gradients: this channel over the 32 positions of the tile; channel c belongs to warp c % 8 only
+                float pw = g[r] * xh, pb = g[r];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    pw += __shfl_xor_sync(kFull, pw, off);
+                    pb += __shfl_xor_sync(kFull, pb, off);
+                }
+                if (lane == 0 && c < C) { s_acc[c] += pw; s_acc[C + c] += pb; }
+            }
         }
+        __syncthreads();                                // previous tile's readers of s_a / s_b are done
+        s_a[wp][lane] = s1;
+        s_b[wp][lane] = s2;
+        __syncthreads();
+        s1 = 0.0f; s2 = 0.0f;
+#pragma unroll
+        for (int i = 0; i < kLnWarps; ++i) { s1 += s_a[i][lane]; s2 += s_b[i][lane]; }
+        const float inv = 1.0f / (float)C;
+        s1 *= inv; s2 *= inv;
+        if (ok)
+            for (int c0 = wp; c0 < C; c0 += kLnWarps * kLnUnroll) {
+                float g[kLnUnroll], xv[kLnUnroll];
+#pragma unroll
+                for (int r = 0; r < kLnUnroll; ++r) {
+                    const int c = c0 + r * kLnWarps;
+                    g[r] = (c < C) ? Elem<T>::to_f(dy[base + (int64_t)c * HW]) : 0.0f;
+                    xv[r] = (c < C) ? Elem<T>::to_f(x[base + (int64_t)c * HW]) : mean;
+                }
+#pragma unroll
+                for (int r = 0; r < kLnUnroll; ++r) {
+                    const int c = c0 + r * kLnWarps;
+                    const float xh = (xv[r] - mean) * rstd;
+                    if (c < C) dx[base + (int64_t)c * HW] = Elem<T>::from_f(rstd * (g[r] * (w ? w[c] : 1.0f) - s1 - xh * s2));
+                }
+            }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kLnWarps * 32) {
+        if (dw) atomicAdd(dw + c, s_acc[c]);
+        if (db) atomicAdd(db + c, s_acc[C + c]);
+    }
 }
 
 int launch_ln2d_fwd(const void* x, const float* w, const float* b, void* y, float* mean, float* rstd, int64_t B, int64_t C,
@@ -115,10 +159,23 @@ int launch_ln2d_fwd(const void* x, const float* w, const float* b, void* y, floa
 
 int launch_ln2d_bwd(const void* x, const void* dy, const float* w, const float* mean, const float* rstd, void* dx, float* dw,
                     float* db, int64_t B, int64_t C, int64_t HW, int dtype, cudaStream_t st) {
-    const unsigned grid = (unsigned)(B * ((HW + kLnPos - 1) / kLnPos));
-    if (dtype == XFS_F32) ln2d_bwd_kernel<float><<<grid, kLnWarps * 32, 0, st>>>((const float*)x, (const float*)dy, w, mean, rstd, (float*)dx, dw, db, (int)C, (int)HW);
-    else if (dtype == XFS_BF16) ln2d_bwd_kernel<__nv_bfloat16><<<grid, kLnWarps * 32, 0, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, w, mean, rstd, (__nv_bfloat16*)dx, dw, db, (int)C, (int)HW);
-    else ln2d_bwd_kernel<__half><<<grid, kLnWarps * 32, 0, st>>>((const __half*)x, (const __half*)dy, w, mean, rstd, (__half*)dx, dw, db, (int)C, (int)HW);
+    const int ntiles = (int)(B * ((HW + kLnPos - 1) / kLnPos));
+    // enough CTAs to fill the machine first (148 SMs x 8 resident CTAs), then fewer flushes
+    int tpc = ntiles / (148 * 8 * 2);
+    tpc = tpc < 1 ? 1 : (tpc > kLnMaxTilesPerCta ? kLnMaxTilesPerCta : tpc);
+    const unsigned grid = (unsigned)((ntiles + tpc - 1) / tpc);
+    const size_t smem = sizeof(float) * 2 * (size_t)C;
+    if (smem > 200 * 1024) return XFS_ERR_UNSUPPORTED;
+    if (dtype == XFS_F32) {
+        cudaFuncSetAttribute(ln2d_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ln2d_bwd_kernel<float><<<grid, kLnWarps * 32, smem, st>>>((const float*)x, (const float*)dy, w, mean, rstd, (float*)dx, dw, db, (int)C, (int)HW, ntiles, tpc);
+    } else if (dtype == XFS_BF16) {
+        cudaFuncSetAttribute(ln2d_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ln2d_bwd_kernel<__nv_bfloat16><<<grid, kLnWarps * 32, smem, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dy, w, mean, rstd, (__nv_bfloat16*)dx, dw, db, (int)C, (int)HW, ntiles, tpc);
+    } else {
+        cudaFuncSetAttribute(ln2d_bwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        ln2d_bwd_kernel<__half><<<grid, kLnWarps * 32, smem, st>>>((const __half*)x, (const __half*)dy, w, mean, rstd, (__half*)dx, dw, db, (int)C, (int)HW, ntiles, tpc);
+    }
     return check_launch();
 }
 
