@@ -18,12 +18,14 @@ struct BwdChunk {            // ADDRESS order, exactly as loaded
     float hstart[kCh];      // kN == 1 only: checkpointed state entering the chunk
 };
 
-template <typename T, typename TDO, int kN, int kCh, bool kFast>
-__global__ void __launch_bounds__(128)
+// kSingle: see ss2d_fwd.cu
+template <typename T, typename TDO, int kN, int kCh, bool kFast, bool kSingle>
+__global__ void __launch_bounds__(128, kSingle ? 5 : 3)
 ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
     extern __shared__ __align__(16) float smem[];
     const int H = (int)p.H, W = (int)p.W, L = H * W;
-    const int Lb = (int)buf_len(L), nch = (L + kChunk - 1) / kChunk;
+    const int Lb = (int)buf_len(L);
+    const int nch = kSingle ? 1 : (L + kChunk - 1) / kChunk;
     const int D = (int)p.D;
     const int N = (kN == 1) ? 1 : (int)p.N;
     const int groups = (D + kCh - 1) / kCh;
@@ -370,12 +372,12 @@ ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
 // ---- host side --------------------------------------------------------------------------------------------------
 constexpr int kChBwd = 1;
 
-template <typename T, typename TDO, int kN, bool kFast>
+template <typename T, typename TDO, int kN, bool kFast, bool kSingle = false>
 static int launch_bwd_k(const xfs_ss2d_bwd_args& a, cudaStream_t st) {
     const size_t smem = bwd_smem(a.H * a.W, a.N, kChBwd);
     const unsigned grid = (unsigned)(a.batch * ((a.D + kChBwd - 1) / kChBwd));
-    if (int rc = set_smem(ss2d_bwd_kernel<T, TDO, kN, kChBwd, kFast>, smem)) return rc;
-    ss2d_bwd_kernel<T, TDO, kN, kChBwd, kFast><<<grid, 128, smem, st>>>(a);
+    if (int rc = set_smem(ss2d_bwd_kernel<T, TDO, kN, kChBwd, kFast, kSingle>, smem)) return rc;
+    ss2d_bwd_kernel<T, TDO, kN, kChBwd, kFast, kSingle><<<grid, 128, smem, st>>>(a);
     return check_launch();
 }
 
@@ -386,6 +388,8 @@ static int launch_bwd_tt(const xfs_ss2d_bwd_args& a, cudaStream_t st) {
     const bool fast = std::is_same<TDO, float>::value && (L % Elem<T>::kVec == 0) && (L % 4 == 0) && aligned16(a.delta) &&
                       aligned16(a.Bs) && aligned16(a.Cs) && aligned16(a.ddelta) && aligned16(a.dBs) && aligned16(a.dCs);
     if constexpr (std::is_same<TDO, float>::value) {
+        if (fast && L <= kChunk)     // one chunk per sequence
+            return a.N == 1 ? launch_bwd_k<T, TDO, 1, true, true>(a, st) : launch_bwd_k<T, TDO, 0, true, true>(a, st);
         if (fast) return a.N == 1 ? launch_bwd_k<T, TDO, 1, true>(a, st) : launch_bwd_k<T, TDO, 0, true>(a, st);
     }
     return a.N == 1 ? launch_bwd_k<T, TDO, 1, false>(a, st) : launch_bwd_k<T, TDO, 0, false>(a, st);

@@ -10,12 +10,15 @@ struct FwdChunk {            // delta/B/C of one chunk of one route, in ADDRESS 
 };
 
 // kN == 1: single state carried in a register; kN == 0: runtime N (<= kFusedMaxState), states carried in smem
-template <typename T, typename TO, int kN, int kCh, bool kFast>
-__global__ void __launch_bounds__(128)
+// kSingle: the sequence fits ONE chunk (L <= 256) -> no chunk loop, no carried state; the leaner code needs fewer
+// registers, so more CTAs fit per SM (these short shapes -- XFMamba's 14x14 stage has 15 of the 21 blocks -- are latency bound)
+template <typename T, typename TO, int kN, int kCh, bool kFast, bool kSingle>
+__global__ void __launch_bounds__(128, kSingle ? 6 : 4)
 ss2d_fwd_kernel(const xfs_ss2d_fwd_args p) {
     extern __shared__ __align__(16) float smem[];
     const int H = (int)p.H, W = (int)p.W, L = H * W;
-    const int Lb = (int)buf_len(L), nch = (L + kChunk - 1) / kChunk;
+    const int Lb = (int)buf_len(L);
+    const int nch = kSingle ? 1 : (L + kChunk - 1) / kChunk;
     const int D = (int)p.D;
     const int N = (kN == 1) ? 1 : (int)p.N;
     const int groups = (D + kCh - 1) / kCh;
@@ -246,12 +249,12 @@ int ss2d_supported(int64_t D, int64_t N, int64_t H, int64_t W, int dtype, int ba
     return (backward ? bwd_smem(L, N, 1) : fwd_smem(L, N, kChFwd)) <= kSmemLimit;
 }
 
-template <typename T, typename TO, int kN, bool kFast>
+template <typename T, typename TO, int kN, bool kFast, bool kSingle = false>
 static int launch_fwd_k(const xfs_ss2d_fwd_args& a, cudaStream_t st) {
     const size_t smem = fwd_smem(a.H * a.W, a.N, kChFwd);
     const unsigned grid = (unsigned)(a.batch * ((a.D + kChFwd - 1) / kChFwd));
-    if (int rc = set_smem(ss2d_fwd_kernel<T, TO, kN, kChFwd, kFast>, smem)) return rc;
-    ss2d_fwd_kernel<T, TO, kN, kChFwd, kFast><<<grid, 128, smem, st>>>(a);
+    if (int rc = set_smem(ss2d_fwd_kernel<T, TO, kN, kChFwd, kFast, kSingle>, smem)) return rc;
+    ss2d_fwd_kernel<T, TO, kN, kChFwd, kFast, kSingle><<<grid, 128, smem, st>>>(a);
     return check_launch();
 }
 
@@ -263,6 +266,8 @@ static int launch_fwd_tt(const xfs_ss2d_fwd_args& a, cudaStream_t st) {
     const bool fast = std::is_same<TO, float>::value && (L % Elem<T>::kVec == 0) && aligned16(a.delta) && aligned16(a.Bs) &&
                       aligned16(a.Cs);
     if constexpr (std::is_same<TO, float>::value) {
+        if (fast && L <= kChunk)     // one chunk per sequence
+            return a.N == 1 ? launch_fwd_k<T, TO, 1, true, true>(a, st) : launch_fwd_k<T, TO, 0, true, true>(a, st);
         if (fast) return a.N == 1 ? launch_fwd_k<T, TO, 1, true>(a, st) : launch_fwd_k<T, TO, 0, true>(a, st);
     }
     return a.N == 1 ? launch_fwd_k<T, TO, 1, false>(a, st) : launch_fwd_k<T, TO, 0, false>(a, st);
