@@ -15,7 +15,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 rep, tag = sys.argv[1], sys.argv[2]
-launches = sys.argv[3] if len(sys.argv) > 3 else None
+launches = sys.argv[3] if len(sys.argv) > 3 and not sys.argv[3].startswith("--") else None
 out_md = os.path.join(ROOT, "profiles", f"{tag}_ncu_summary.md")
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
@@ -77,5 +77,6 @@ if launches and os.path.exists(launches):
     md += ["## launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`, cold cache, serialised)", "",
            f"see `profiles/{tag}_launches.csv`", ""]
 open(out_md, "w").write("\n".join(md))
-json.dump(traffic, open(traffic_path, "w"), indent=1)
+if "--no-traffic" not in sys.argv:      # traffic.json carries the headline (config-2) workload only
+    json.dump(traffic, open(traffic_path, "w"), indent=1)
 print(out_md)
