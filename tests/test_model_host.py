@@ -113,3 +113,31 @@ def test_published_variants_instantiate_with_reference_parameter_counts(variant,
         m = TwoViewXFMamba(outputs=2, type=variant)
     n = sum(p.numel() for p in m.parameters()) / 1e6
     assert abs(n - params_m) < 0.01, n
+
+
+@pytest.mark.gpu
+def test_config1_xfmamba_t_two_pairs_gpu_vs_cpu_oracle_path(monkeypatch):
+    """BASELINE.json config 1: XFMamba-T forward on 2 synthetic two-view 224x224 pairs, random init (seed 0).
+    The reference's weights cannot travel, so parity is checked at full size between the CUDA path and the SAME network
+    evaluated on the host with the CPU oracle substituted for every scan operator (32 scan calls: 4 stages x blocks x 2
+    views + shallow + 3 deep-fusion streams)."""
+    import time
+    import xfmamba_b200.model as M
+    from xfmamba_b200.model import TwoViewXFMamba
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.manual_seed(0)
+    m = TwoViewXFMamba(outputs=2, type="tiny").eval()
+    xa, xb = torch.randn(2, 1, 224, 224), torch.randn(2, 1, 224, 224)
+    dev = torch.device("cuda:0")
+    with torch.no_grad():
+        got = m.to(dev)(xa.to(dev), xb.to(dev)).cpu()
+    m = m.cpu()
+    for name in ("ss2d_scan", "cross_scan_fn", "selective_scan_fn", "swapping_scan", "swapping_merge", "layer_norm_2d"):
+        monkeypatch.setattr(M.OPS, name, getattr(OracleOps, name))
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        want = m(xa, xb)
+    print(f"config 1 on the host (torch CPU dense layers + oracle scans): {time.perf_counter() - t0:.2f} s for 2 pairs")
+    assert got.shape == (2, 2)
+    assert rel_err(got.numpy(), want.numpy()) < 1e-4
