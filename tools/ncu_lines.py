@@ -53,6 +53,7 @@ def main():
     ap.add_argument("--so", default=os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "xfmamba_b200", "libxfscan.so"))
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--sass", action="store_true", help="also list the hottest SASS instructions")
+    ap.add_argument("--fn", default=None, help="regex on the MANGLED cubin function name (default: derived from `kernel`; needed when several instantiations have similar sizes)")
     ap.add_argument("--op", default=None, help="only count SASS instructions whose opcode matches this regex (e.g. 'IMAD.MOV|^MOV')")
     a = ap.parse_args()
 
@@ -68,7 +69,7 @@ def main():
     ix = {h: i for i, h in enumerate(hdr)}
     data = [r for r in rows[1:] if len(r) > ix["# Samples"] and r[0].startswith("0x")]
     base = int(data[0][0], 16)
-    mangled_hint = re.sub(r"\W+", ".*", a.kernel)
+    mangled_hint = a.fn or re.sub(r"\W+", ".*", a.kernel)
     maps = sass_line_map(a.so, mangled_hint)
     # choose the function whose instruction count matches
     best = None

@@ -86,8 +86,17 @@ ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
     auto walk = [&](auto rev_tag) __attribute__((always_inline)) {
         constexpr bool rev = decltype(rev_tag)::value;     // the FORWARD walk direction of this route
 
+        const T* pf_row = (kN != 1 || kCh != 1 || kSingle || lane >= 24) ? nullptr : (lane < 8) ? dt_row[0] : (lane < 16) ? Bk : Ck;
+
         auto load_chunk = [&](int step, BwdChunk<kN, kCh>& c) __attribute__((always_inline)) {
             const int j = rev ? step : (nch - 1 - step);
+            if (kN == 1 && kCh == 1 && !kSingle) {
+                if (step == 0) {
+#pragma unroll
+                    for (int a = 1; a < kPrefetchAhead; ++a) prefetch_chunk_l2<T>(pf_row, rev, rev ? j + a : j - a, nch, L, lane);
+                }
+                prefetch_chunk_l2<T>(pf_row, rev, rev ? j + kPrefetchAhead : j - kPrefetchAhead, nch, L, lane);
+            }
             const int p0 = j * kChunk + lane * kItems;
             const int l0 = rev ? L - 8 - p0 : p0;
             const int jprev = rev ? j + 1 : j - 1;           // chunk the forward walked just before this one
@@ -166,7 +175,7 @@ ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
                     B2[jj] = add2(B2[jj], splat2(rt_zero));          // private copy: B is needed again for du
                 }
             }
-            if (step + 1 < nch) load_chunk(step + 1, c);
+            if (!kSingle) load_chunk(min(step + 1, nch - 1), c);   // unconditional, see ss2d_fwd.cu
 
             f2 dt2[kCh][4], sig2[kCh][4], du2[kCh][4], ddt2[kCh][4];
 #pragma unroll

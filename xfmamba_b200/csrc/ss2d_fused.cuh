@@ -71,6 +71,21 @@ __device__ __forceinline__ void row_store8(T* __restrict__ row, int l0, int L, b
     else store8<T>(row, l0, L, vec_ok, v);
 }
 
+// ---- L2 prefetch of the streamed rows ----------------------------------------------------------------------------
+// The register prefetch is one chunk deep (more would cost registers, i.e. occupancy), which leaves too few bytes in
+// flight to cover DRAM latency.  ONE extra instruction per chunk pulls the delta / B / C rows of a chunk further ahead
+// into L2 (lanes 0-7 / 8-15 / 16-23 take the 128-byte lines of one row each), so the register loads that follow hit L2.
+constexpr int kPrefetchAhead = 2;    // chunks beyond the one being loaded into registers
+
+template <typename T>
+__device__ __forceinline__ void prefetch_chunk_l2(const T* lane_row, bool flipped, int j, int nch, int L, int lane) {
+    constexpr int kLine = 128 / (int)sizeof(T);                    // elements per line
+    const int start = flipped ? L - kChunk * (j + 1) : kChunk * j; // scan index of the chunk's lowest address
+    const int off = start + (lane & 7) * kLine;
+    if (lane_row != nullptr && j >= 0 && j < nch && (lane & 7) * kLine < kChunk && off >= 0 && off < L)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(lane_row + off));
+}
+
 // ---- short sequences (L <= 64): one sequence per 8-lane group, see ss2d_small.cu ---------------------------------
 constexpr int kSmallL = 64;          // positions per sequence slot
 constexpr int kSmallMaxN = 16;

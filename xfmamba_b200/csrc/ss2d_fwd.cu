@@ -68,20 +68,57 @@ ss2d_fwd_kernel(const xfs_ss2d_fwd_args p) {
     auto walk = [&](auto rev_tag) __attribute__((always_inline)) {
         constexpr bool rev = decltype(rev_tag)::value;
 
-        auto load_chunk = [&](int step, FwdChunk<kN, kCh>& c) __attribute__((always_inline)) {
+        // Only the LAST chunk (spatial positions >= L) has 16-byte granules outside the rows.  Its clamped per-lane
+        // offsets are computed once, so the loads of every other chunk carry no range checks (kFast); a flipped route
+        // meets that chunk first -- in the peeled load below -- so its in-loop loads need no select at all.
+        const int p0_last = (nch - 1) * kChunk + lane * kItems;
+        const int l0_last = rev ? L - 8 - p0_last : p0_last;
+        const int g0_last = (l0_last >= 0 && l0_last + 4 <= L) ? l0_last : 0;
+        const int g1_last = (l0_last + 4 >= 0 && l0_last + 8 <= L) ? l0_last + 4 : 0;
+
+        const T* pf_row = (kN != 1 || kCh != 1 || kSingle || lane >= 24) ? nullptr : (lane < 8) ? dt_row[0] : (lane < 16) ? Bk : Ck;
+
+        auto load_chunk = [&](int step, FwdChunk<kN, kCh>& c, auto peeled_tag) __attribute__((always_inline)) {
+            constexpr bool peeled = decltype(peeled_tag)::value;
             const int j = rev ? (nch - 1 - step) : step;
+            if (kN == 1 && kCh == 1 && !kSingle) {
+                if (peeled) {
+#pragma unroll
+                    for (int a = 1; a < kPrefetchAhead; ++a) prefetch_chunk_l2<T>(pf_row, rev, rev ? j - a : j + a, nch, L, lane);
+                }
+                prefetch_chunk_l2<T>(pf_row, rev, rev ? j - kPrefetchAhead : j + kPrefetchAhead, nch, L, lane);
+            }
             const int p0 = j * kChunk + lane * kItems;
             const int l0 = rev ? L - 8 - p0 : p0;        // scan index of the lowest-address element
+            if constexpr (kFast && Elem<T>::kVec == 4) {
+                const bool last = rev ? peeled : (j == nch - 1);
+                const int g0 = last ? g0_last : l0, g1 = last ? g1_last : l0 + 4;
 #pragma unroll
-            for (int ch = 0; ch < kCh; ++ch) row_load8<T, kFast>(dt_row[ch], l0, L, vin, c.dt[ch]);
-            if (kN == 1) {
-                row_load8<T, kFast>(Bk, l0, L, vin, c.B);
-                row_load8<T, kFast>(Ck, l0, L, vin, c.C);
+                for (int ch = 0; ch < kCh; ++ch) load8_at<T>(dt_row[ch], g0, g1, c.dt[ch]);
+                if (kN == 1) { load8_at<T>(Bk, g0, g1, c.B); load8_at<T>(Ck, g0, g1, c.C); }
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < kCh; ++ch) row_load8<T, kFast>(dt_row[ch], l0, L, vin, c.dt[ch]);
+                if (kN == 1) {
+                    row_load8<T, kFast>(Bk, l0, L, vin, c.B);
+                    row_load8<T, kFast>(Ck, l0, L, vin, c.C);
+                }
+            }
+            if (rev && peeled) {
+                // positions >= L come FIRST in a flipped route and must be identity maps (dt = 0): softplus(-inf) = 0,
+                // and without softplus dt = (-bias) + bias = 0.  Done here, once, instead of masking inside every chunk.
+#pragma unroll
+                for (int ch = 0; ch < kCh; ++ch) {
+                    const float off = p.delta_softplus ? -INFINITY : -bias[ch];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (l0 + i < 0) c.dt[ch][i] = off;
+                }
             }
         };
 
         FwdChunk<kN, kCh> c0;           // ONE register set: re-loaded for the next chunk as soon as this one is consumed
-        load_chunk(0, c0);              // in flight while the image is staged
+        load_chunk(0, c0, std::true_type{});   // in flight while the image is staged
         {
             const T* __restrict__ x = reinterpret_cast<const T*>(p.x);
 #pragma unroll
@@ -99,7 +136,6 @@ ss2d_fwd_kernel(const xfs_ss2d_fwd_args p) {
             const int l0 = rev ? L - 8 - p0 : p0;
             const int f4s = swz_f4(p0 >> 2);
             const bool in_buf = p0 < Lb;                    // lane has shared-memory backing
-            const bool tail = p0 + 8 > L;
 
             // ---- read every load register once (dt -> dt + bias, B -> B*u, C -> C + 0), then re-load the SAME registers
             // with the next chunk: the loads fly during the whole computation below (scoreboard note in the header)
@@ -143,14 +179,9 @@ ss2d_fwd_kernel(const xfs_ss2d_fwd_args p) {
                     dt2[ch][jj] = p.delta_softplus ? softplus2(xx, e) : xx;
                     y2[ch][jj] = mul2(splat2(Dd[ch]), u2[ch][jj]);
                 }
-                if (tail) {                                   // positions >= L: identity map (dt = 0)
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        if (p0 + 2 * jj >= L) dt2[ch][jj].x = 0.0f;
-                        if (p0 + 2 * jj + 1 >= L) dt2[ch][jj].y = 0.0f;
-                    }
-                }
             }
+            // positions >= L (last chunk only): a forward route meets them after every real position, so whatever they hold
+            // never reaches a real one; a flipped route had them turned into identity maps by the peeled load.
             for (int n = 0; n < N; ++n) {
                 f2 C2[4];
                 if (kN == 1) {
@@ -225,7 +256,9 @@ ss2d_fwd_kernel(const xfs_ss2d_fwd_args p) {
 
 #pragma unroll 1
         for (int step = 0; step < nch; ++step)
-            compute_chunk(step, c0, [&]() __attribute__((always_inline)) { if (step + 1 < nch) load_chunk(step + 1, c0); });
+            // the re-load is UNCONDITIONAL (the last step re-reads its own chunk, an L1 hit): a conditional one keeps the old
+            // values formally alive across the whole step and costs two register-to-register copies of the set per chunk
+            compute_chunk(step, c0, [&]() __attribute__((always_inline)) { if (!kSingle) load_chunk(min(step + 1, nch - 1), c0, std::false_type{}); });
     };  // walk
     if (k >= 2) walk(std::true_type{}); else walk(std::false_type{});
     if (!synced) pair_barrier(k & 1);

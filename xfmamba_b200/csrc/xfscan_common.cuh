@@ -152,6 +152,15 @@ __device__ __forceinline__ void load8_fast(const T* __restrict__ row, int l0, in
     }
 }
 
+// fp32 rows, offsets of the two granules already resolved by the caller (see ss2d_fwd.cu: only one chunk per route needs clamping)
+template <typename T>
+__device__ __forceinline__ void load8_at(const T* __restrict__ row, int g0, int g1, float (&v)[8]) {
+    static_assert(Elem<T>::kVec == 4, "fp32 rows only");
+    const uint4 a = ldg16(row + g0), b = ldg16(row + g1);
+    v[0] = __uint_as_float(a.x); v[1] = __uint_as_float(a.y); v[2] = __uint_as_float(a.z); v[3] = __uint_as_float(a.w);
+    v[4] = __uint_as_float(b.x); v[5] = __uint_as_float(b.y); v[6] = __uint_as_float(b.z); v[7] = __uint_as_float(b.w);
+}
+
 template <typename T>
 __device__ __forceinline__ void store8_fast(T* __restrict__ row, int l0, int L, const float (&v)[8]) {
     if constexpr (Elem<T>::kVec == 4) {
