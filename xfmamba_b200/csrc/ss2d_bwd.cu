@@ -230,7 +230,7 @@ ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
                     float a[8], bu[8], cd[8], S[8], P[8], Sq[8], Pq[8];
                     const float h_start = (kN == 1) ? hst[ch]
                                                     : ((jprev >= 0 && jprev < nch) ? st_row[ch][jprev * N + n] : 0.0f);
-                    float unused, q_out;
+                    float q_out;
                     float* qs = s_q + (k * kCh + ch) * kFusedMaxState + n;
                     const float qc = (kN == 1) ? qcarry1[ch] : *qs;
 #pragma unroll
@@ -246,14 +246,14 @@ ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
                         const int i = rev ? 7 - ii : ii;
                         Sr = fmaf(a[i], Sr, bu[i]); Pr *= a[i]; S[i] = Sr; P[i] = Pr;
                     }
-                    const float h_in = warp_prefix<rev>(Pr, Sr, h_start, lane, unused);
-                    Pr = 1.0f; Sr = 0.0f;
+                    float Pqr = 1.0f, Sqr = 0.0f;
 #pragma unroll
                     for (int ii = 0; ii < 8; ++ii) {
                         const int i = rev ? ii : 7 - ii;
-                        Sr = a[i] * (cd[i] + Sr); Pr *= a[i]; Sq[i] = Sr; Pq[i] = Pr;
+                        Sqr = a[i] * (cd[i] + Sqr); Pqr *= a[i]; Sq[i] = Sqr; Pq[i] = Pqr;
                     }
-                    const float q_in = warp_prefix<!rev>(Pr, Sr, qc, lane, q_out);
+                    float h_in, q_in;
+                    warp_prefix_dual<rev>(Pr, Sr, h_start, Pqr, Sqr, qc, lane, h_in, q_in, q_out);
                     pack8(S, S2); pack8(P, P2); pack8(Sq, Sq2); pack8(Pq, Pq2);
                     // element-wise part on packed pairs
                     f2 q2[4], gi2[4];

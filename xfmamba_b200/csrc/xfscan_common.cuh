@@ -216,6 +216,31 @@ __device__ __forceinline__ float warp_prefix(float P, float S, float carry, int 
     return first ? carry : prev;
 }
 
+// Two independent scans in one pass -- the forward re-scan along the walk direction kRev and the adjoint scan against
+// it, as the backward needs them for every chunk.  Shuffles are ordered with respect to each other, so two back-to-back
+// warp_prefix calls serialise their 7 round trips each; interleaved, the rounds of one hide the latency of the other.
+template <bool kRev>
+__device__ __forceinline__ void warp_prefix_dual(float P, float S, float carry, float Pq, float Sq, float qcarry, int lane,
+                                                 float& h_in, float& q_in, float& q_out) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const float Pn = kRev ? __shfl_down_sync(kFull, P, off) : __shfl_up_sync(kFull, P, off);
+        const float Sn = kRev ? __shfl_down_sync(kFull, S, off) : __shfl_up_sync(kFull, S, off);
+        const float Pqn = kRev ? __shfl_up_sync(kFull, Pq, off) : __shfl_down_sync(kFull, Pq, off);
+        const float Sqn = kRev ? __shfl_up_sync(kFull, Sq, off) : __shfl_down_sync(kFull, Sq, off);
+        const bool has = kRev ? (lane + off < 32) : (lane >= off);
+        const bool hasq = kRev ? (lane >= off) : (lane + off < 32);
+        if (has) { S = fmaf(P, Sn, S); P = P * Pn; }
+        if (hasq) { Sq = fmaf(Pq, Sqn, Sq); Pq = Pq * Pqn; }
+    }
+    const float incl = fmaf(P, carry, S), inclq = fmaf(Pq, qcarry, Sq);
+    const float prev = kRev ? __shfl_down_sync(kFull, incl, 1) : __shfl_up_sync(kFull, incl, 1);
+    const float prevq = kRev ? __shfl_up_sync(kFull, inclq, 1) : __shfl_down_sync(kFull, inclq, 1);
+    q_out = __shfl_sync(kFull, inclq, kRev ? 31 : 0);
+    h_in = (kRev ? (lane == 31) : (lane == 0)) ? carry : prev;
+    q_in = (kRev ? (lane == 0) : (lane == 31)) ? qcarry : prevq;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // packed fp32 (sm_100 FFMA2 / FMUL2 / FADD2: two fp32 lanes per issue slot on a 64-bit register pair)
 // ---------------------------------------------------------------------------------------------------------
