@@ -202,6 +202,19 @@ XFS_API int xfs_layernorm2d_bwd(const void* x, const void* dy, const float* weig
                                 void* dx, float* dweight, float* dbias, int64_t B, int64_t C, int64_t HW, int dtype,
                                 xfs_stream_t stream);
 
+/* -------------------------------------------------------------------------------------------------------------
+ * Depthwise 3x3 convolution (stride 1, zero padding 1) fused with SiLU: the producer of the scan input in every SS2D
+ * block (reference nn.Conv2d(groups=d_inner) + act, models/fusion_vmamba.py:405-413,1199-1200; :595-601; :855-858).
+ * x, y, dy, dx: (B, C, H, W) dtype, contiguous; weight: (C, 1, 3, 3) f32; bias: (C) f32 or NULL; act: 1 = SiLU, 0 = none.
+ * bwd writes dx and per-plane partial sums part: (B*C, 10) f32 = 9 filter taps + bias; the caller sums over B
+ * (deterministic, no global atomics).  xfs_dwconv3x3_supported: 0 when a plane does not fit shared memory.
+ * ----------------------------------------------------------------------------------------------------------- */
+XFS_API int xfs_dwconv3x3_supported(int64_t H, int64_t W, int backward);
+XFS_API int xfs_dwconv3x3_fwd(const void* x, const float* weight, const float* bias, void* y, int64_t B, int64_t C, int64_t H,
+                              int64_t W, int dtype, int act, xfs_stream_t stream);
+XFS_API int xfs_dwconv3x3_bwd(const void* x, const float* weight, const float* bias, const void* dy, void* dx, float* part,
+                              int64_t B, int64_t C, int64_t H, int64_t W, int dtype, int act, xfs_stream_t stream);
+
 /* number of kernels this library has launched since load (process-wide, relaxed atomic): lets bench.py report
  * `gpu_launches` from a count instead of a guess */
 XFS_API int64_t xfs_launch_count(void);

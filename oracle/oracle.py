@@ -16,6 +16,7 @@ import numpy as np
 __all__ = [
     "build", "lib", "route_table", "cross_scan", "cross_merge", "cross_merge_1b1", "swap_scan", "swap_merge",
     "selective_scan_fwd", "selective_scan_bwd", "ss2d_fwd", "ss2d_bwd", "bf16_round", "np_cross_scan", "layernorm2d",
+    "dwconv3x3_silu", "dwconv3x3_silu_bwd",
 ]
 
 _HERE = Path(__file__).resolve().parent
@@ -207,6 +208,47 @@ def layernorm2d(x, weight=None, bias=None, eps=1e-5):
     if bias is not None:
         y = y + np.asarray(bias, dtype=np.float64).reshape(shp)
     return y
+
+
+def _dw_shift(xp, i, j, H, W):
+    return xp[:, :, i:i + H, j:j + W]
+
+
+def dwconv3x3_silu(x, weight, bias=None, act=True):
+    """``act(conv2d(x))`` with a depthwise 3x3, padding-1 convolution (nn.Conv2d(groups=d_inner) + SiLU,
+    models/fusion_vmamba.py:405-413,1199-1200), in float64.  x (B, C, H, W); weight (C, 1, 3, 3); bias (C) or None."""
+    x64 = np.asarray(x, dtype=np.float64)
+    w = np.asarray(weight, dtype=np.float64).reshape(-1, 3, 3)
+    B, C, H, W = x64.shape
+    xp = np.pad(x64, ((0, 0), (0, 0), (1, 1), (1, 1)))
+    pre = np.zeros_like(x64)
+    for i in range(3):
+        for j in range(3):
+            pre += _dw_shift(xp, i, j, H, W) * w[None, :, i, j, None, None]
+    if bias is not None:
+        pre += np.asarray(bias, dtype=np.float64)[None, :, None, None]
+    return pre / (1.0 + np.exp(-pre)) if act else pre
+
+
+def dwconv3x3_silu_bwd(x, weight, bias, dy, act=True):
+    """gradients of dwconv3x3_silu: returns (dx, dweight (C,1,3,3), dbias (C)) in float64"""
+    x64 = np.asarray(x, dtype=np.float64)
+    w = np.asarray(weight, dtype=np.float64).reshape(-1, 3, 3)
+    B, C, H, W = x64.shape
+    pre = dwconv3x3_silu(x64, w, bias, act=False)
+    g = np.asarray(dy, dtype=np.float64)
+    if act:
+        s = 1.0 / (1.0 + np.exp(-pre))
+        g = g * s * (1.0 + pre * (1.0 - s))
+    xp = np.pad(x64, ((0, 0), (0, 0), (1, 1), (1, 1)))
+    gp = np.pad(g, ((0, 0), (0, 0), (1, 1), (1, 1)))
+    dx = np.zeros_like(x64)
+    dw = np.zeros((C, 3, 3))
+    for i in range(3):
+        for j in range(3):
+            dx += _dw_shift(gp, 2 - i, 2 - j, H, W) * w[None, :, i, j, None, None]
+            dw[:, i, j] = (g * _dw_shift(xp, i, j, H, W)).sum(axis=(0, 2, 3))
+    return dx, dw.reshape(C, 1, 3, 3), g.sum(axis=(0, 2, 3))
 
 
 def bf16_round(a: np.ndarray) -> np.ndarray:

@@ -425,3 +425,50 @@ def test_layernorm2d_matches_reference_layernorm2d(xf, shape, dtype):
     assert rel_err(n(x.grad), n(xr.grad)) < (1e-4 if dtype == torch.float32 else 2e-2)
     assert rel_err(n(w.grad), n(wr.grad)) < (1e-4 if dtype == torch.float32 else 2e-2)
     assert rel_err(n(b.grad), n(br.grad)) < (1e-4 if dtype == torch.float32 else 2e-2)
+
+
+# ---- depthwise 3x3 conv + SiLU: the producer of the scan input (reference models/fusion_vmamba.py:405-413,1199-1200) ----
+@pytest.mark.parametrize("shape,bias,act", [
+    ((2, 5, 7, 7), True, True), ((3, 20, 14, 14), False, True), ((2, 11, 28, 28), True, True), ((2, 3, 56, 56), False, True),
+    ((1, 2, 57, 58), True, True), ((1, 1, 128, 128), True, True), ((2, 4, 16, 16), True, False), ((1, 70, 7, 7), False, True),
+    ((2, 9, 13, 5), True, True),
+])
+def test_dwconv3x3_silu_fwd_bwd_vs_oracle(shape, bias, act):
+    from xfmamba_b200.conv import dwconv3x3_silu
+    rng = np.random.default_rng(sum(shape))
+    B, C, H, W = shape
+    x = rng.standard_normal(shape).astype(np.float32)
+    w = (rng.standard_normal((C, 1, 3, 3)) * 0.4).astype(np.float32)
+    b = rng.standard_normal(C).astype(np.float32) if bias else None
+    dy = rng.standard_normal(shape).astype(np.float32)
+    xt, wt = t(x).requires_grad_(), t(w).requires_grad_()
+    bt = t(b).requires_grad_() if bias else None
+    y = dwconv3x3_silu(xt, wt, bt, act)
+    y.backward(t(dy))
+    assert rel_err(n(y), oracle.dwconv3x3_silu(x, w, b, act)) < TOL32
+    dx, dw, db = oracle.dwconv3x3_silu_bwd(x, w, b, dy, act)
+    assert rel_err(n(xt.grad), dx) < TOL32
+    assert rel_err(n(wt.grad), dw) < TOL32
+    if bias:
+        assert rel_err(n(bt.grad), db) < TOL32
+
+
+def test_dwconv3x3_silu_bf16_and_torch_agreement():
+    import torch.nn.functional as F
+    from xfmamba_b200.conv import dwconv3x3_silu
+    torch.manual_seed(3)
+    x = torch.randn(4, 24, 28, 28, device=dev())
+    w = torch.randn(24, 1, 3, 3, device=dev()) * 0.3
+    b = torch.randn(24, device=dev())
+    ref = oracle.dwconv3x3_silu(n(x.bfloat16()), n(w), n(b))
+    got = dwconv3x3_silu(x.bfloat16(), w, b)
+    assert got.dtype == torch.bfloat16
+    assert rel_err(n(got), ref) < TOL16
+    torch.backends.cudnn.allow_tf32 = False
+    assert rel_err(n(dwconv3x3_silu(x, w, b)), n(F.silu(F.conv2d(x, w, b, padding=1, groups=24)))) < TOL32
+
+
+def test_dwconv3x3_rejects_cpu_tensors():
+    from xfmamba_b200.conv import dwconv3x3_silu
+    with pytest.raises(RuntimeError):
+        dwconv3x3_silu(torch.randn(1, 2, 4, 4), torch.randn(2, 1, 3, 3))

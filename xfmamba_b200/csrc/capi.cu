@@ -21,6 +21,10 @@ int launch_ss2d_small_bwd(const xfs_ss2d_bwd_args&, cudaStream_t);
 int launch_ln2d_fwd(const void*, const float*, const float*, void*, float*, float*, int64_t, int64_t, int64_t, float, int, cudaStream_t);
 int launch_ln2d_bwd(const void*, const void*, const float*, const float*, const float*, void*, float*, float*, int64_t, int64_t, int64_t, int, cudaStream_t);
 
+int dwconv_supported(int64_t, int64_t, int);
+int launch_dwconv_fwd(const void*, const float*, const float*, void*, int64_t, int64_t, int64_t, int64_t, int, int, cudaStream_t);
+int launch_dwconv_bwd(const void*, const float*, const float*, const void*, void*, float*, int64_t, int64_t, int64_t, int64_t, int, int, cudaStream_t);
+
 static std::atomic<long long> g_launches{0};
 
 int check_launch() {
@@ -164,6 +168,24 @@ int xfs_layernorm2d_bwd(const void* x, const void* dy, const float* weight, cons
     if (B <= 0 || C <= 0 || HW <= 0) return XFS_ERR_SHAPE;
     if (bad_dtype(dtype)) return XFS_ERR_DTYPE;
     return launch_ln2d_bwd(x, dy, weight, mean, rstd, dx, dweight, dbias, B, C, HW, dtype, (cudaStream_t)stream);
+}
+
+int xfs_dwconv3x3_supported(int64_t H, int64_t W, int backward) { return dwconv_supported(H, W, backward); }
+
+int xfs_dwconv3x3_fwd(const void* x, const float* weight, const float* bias, void* y, int64_t B, int64_t C, int64_t H, int64_t W,
+                      int dtype, int act, xfs_stream_t stream) {
+    if (!x || !weight || !y) return XFS_ERR_NULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return XFS_ERR_SHAPE;
+    if (bad_dtype(dtype)) return XFS_ERR_DTYPE;
+    return launch_dwconv_fwd(x, weight, bias, y, B, C, H, W, dtype, act != 0, (cudaStream_t)stream);
+}
+
+int xfs_dwconv3x3_bwd(const void* x, const float* weight, const float* bias, const void* dy, void* dx, float* part, int64_t B,
+                      int64_t C, int64_t H, int64_t W, int dtype, int act, xfs_stream_t stream) {
+    if (!x || !weight || !dy || !dx || !part) return XFS_ERR_NULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return XFS_ERR_SHAPE;
+    if (bad_dtype(dtype)) return XFS_ERR_DTYPE;
+    return launch_dwconv_bwd(x, weight, bias, dy, dx, part, B, C, H, W, dtype, act != 0, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -28,7 +28,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import csm, csms6s, fusion_ops, norm
+from . import conv, csm, csms6s, fusion_ops, norm
 
 OPS = types.SimpleNamespace(
     ss2d_scan=fusion_ops.ss2d_scan,
@@ -37,6 +37,7 @@ OPS = types.SimpleNamespace(
     swapping_scan=fusion_ops.SwappingScan_multiview.apply,
     swapping_merge=fusion_ops.SwappingMerge_multiview.apply,
     layer_norm_2d=norm.layer_norm_2d,
+    dwconv3x3_silu=conv.dwconv3x3_silu,
 )
 
 VARIANTS = {   # reference net_fusionmamba.py:151-159
@@ -153,7 +154,7 @@ class SS2D(nn.Module):
         _ssm_params(self, d_state, self.dt_rank, self.d_inner, 4)
 
     def forward(self, x):
-        x = F.silu(self.conv2d(self.in_proj(x)))
+        x = OPS.dwconv3x3_silu(self.in_proj(x), self.conv2d.weight, self.conv2d.bias)
         B, D, H, W = x.shape
         y = ss2d_core(x, self.x_proj_weight, self.dt_projs_weight, self.dt_projs_bias, self.A_logs, self.Ds)
         y = self.out_norm(y.view(B, D, H, W)).to(x.dtype)
@@ -245,7 +246,8 @@ class ShallowFuseSS2D(nn.Module):
     def forward(self, x, x2):                                   # (B, H, W, C)
         xp = self.in_proj(x).permute(0, 3, 1, 2).contiguous()
         x2p = self.in_proj(x2).permute(0, 3, 1, 2).contiguous()
-        xc, x2c = F.silu(self.conv2d(xp)), F.silu(self.conv2d(x2p))
+        xc = OPS.dwconv3x3_silu(xp, self.conv2d.weight, self.conv2d.bias)
+        x2c = OPS.dwconv3x3_silu(x2p, self.conv2d.weight, self.conv2d.bias)
         B, D, H, W = xc.shape
         y, y2 = shallow_fuse_core(xc, x2c, self.x_proj_weight, self.dt_projs_weight, self.dt_projs_bias, self.A_logs, self.Ds)
         to_last = lambda t: t.view(B, D, H * W).transpose(1, 2).reshape(B, H, W, D)
@@ -287,7 +289,7 @@ class CrossSS2D(nn.Module):
     def forward(self, x, x2):                                   # (B, H, W, C)
         xf = self.in_proj_sec((x + x2) / 2)
         z = F.silu(xf)
-        prep = lambda t: F.silu(self.conv2d(t.permute(0, 3, 1, 2).contiguous()))
+        prep = lambda t: OPS.dwconv3x3_silu(t.permute(0, 3, 1, 2).contiguous(), self.conv2d.weight, self.conv2d.bias)
         xc, x2c, xfc = prep(self.in_proj_sec(x)), prep(self.in_proj_sec(x2)), prep(xf)
         B, D, H, W = xc.shape
         ys = cross_fuse_core(xc, x2c, xfc, self.x_proj_weight, self.dt_projs_weight, self.dt_projs_bias, self.A_logs, self.Ds)
