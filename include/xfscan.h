@@ -215,6 +215,15 @@ XFS_API int xfs_dwconv3x3_fwd(const void* x, const float* weight, const float* b
 XFS_API int xfs_dwconv3x3_bwd(const void* x, const float* weight, const float* bias, const void* dy, void* dx, float* part,
                               int64_t B, int64_t C, int64_t H, int64_t W, int dtype, int act, xfs_stream_t stream);
 
+/* -------------------------------------------------------------------------------------------------------------
+ * Low-rank delta projection of the SS2D core (reference F.conv1d(dts_r, dt_projs_weight, groups=K),
+ * models/fusion_vmamba.py:1155-1157; einsum at :818):  delta[b, k*D + d, l] = sum_r W[k, d, r] * z[b, k, r, l].
+ * z: rows of L contiguous elements at z + b*z_batch_stride + k*z_route_stride + r*L (a slice of the x_proj output is
+ * accepted as it lies); W: (K, D, R) f32, R <= 64; delta: (B, K*D, L) dtype, contiguous.
+ * ----------------------------------------------------------------------------------------------------------- */
+XFS_API int xfs_dt_proj_fwd(const void* z, const float* W, void* delta, int64_t B, int64_t K, int64_t D, int64_t R, int64_t L,
+                            int64_t z_batch_stride, int64_t z_route_stride, int dtype, xfs_stream_t stream);
+
 /* number of kernels this library has launched since load (process-wide, relaxed atomic): lets bench.py report
  * `gpu_launches` from a count instead of a guess */
 XFS_API int64_t xfs_launch_count(void);

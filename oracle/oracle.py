@@ -16,7 +16,7 @@ import numpy as np
 __all__ = [
     "build", "lib", "route_table", "cross_scan", "cross_merge", "cross_merge_1b1", "swap_scan", "swap_merge",
     "selective_scan_fwd", "selective_scan_bwd", "ss2d_fwd", "ss2d_bwd", "bf16_round", "np_cross_scan", "layernorm2d",
-    "dwconv3x3_silu", "dwconv3x3_silu_bwd",
+    "dwconv3x3_silu", "dwconv3x3_silu_bwd", "dt_proj", "dt_proj_bwd",
 ]
 
 _HERE = Path(__file__).resolve().parent
@@ -249,6 +249,22 @@ def dwconv3x3_silu_bwd(x, weight, bias, dy, act=True):
             dx += _dw_shift(gp, 2 - i, 2 - j, H, W) * w[None, :, i, j, None, None]
             dw[:, i, j] = (g * _dw_shift(xp, i, j, H, W)).sum(axis=(0, 2, 3))
     return dx, dw.reshape(C, 1, 3, 3), g.sum(axis=(0, 2, 3))
+
+
+def dt_proj(z, weight):
+    """delta[b, k*D + d, l] = sum_r W[k, d, r] z[b, k, r, l]  (F.conv1d(dts_r, dt_projs_weight, groups=K),
+    models/fusion_vmamba.py:1155-1157), float64.  z (B, K, R, L); weight (K, D, R) -> (B, K*D, L)"""
+    z64, w64 = np.asarray(z, dtype=np.float64), np.asarray(weight, dtype=np.float64)
+    B, K, R, L = z64.shape
+    return np.einsum("bkrl,kdr->bkdl", z64, w64).reshape(B, -1, L)
+
+
+def dt_proj_bwd(z, weight, g):
+    """gradients of dt_proj: (dz (B, K, R, L), dweight (K, D, R)), float64"""
+    z64, w64 = np.asarray(z, dtype=np.float64), np.asarray(weight, dtype=np.float64)
+    B, K, R, L = z64.shape
+    g4 = np.asarray(g, dtype=np.float64).reshape(B, K, -1, L)
+    return np.einsum("bkdl,kdr->bkrl", g4, w64), np.einsum("bkdl,bkrl->kdr", g4, z64)
 
 
 def bf16_round(a: np.ndarray) -> np.ndarray:

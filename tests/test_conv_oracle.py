@@ -26,3 +26,18 @@ def test_oracle_dwconv_matches_torch(shape, bias):
     assert rel_err(dw, w.grad.numpy()) < 1e-12
     if bias:
         assert rel_err(db, b.grad.numpy()) < 1e-12
+
+
+def test_oracle_dt_proj_matches_torch_grouped_conv1d():
+    """the reference's formulation: F.conv1d(dts_r.view(B, K*R, L), W.view(K*D, R, 1), groups=K) (models/fusion_vmamba.py:1155-1157)"""
+    torch.manual_seed(5)
+    B, K, R, D, L = 2, 4, 3, 10, 21
+    z = torch.randn(B, K, R, L, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(K, D, R, dtype=torch.float64, requires_grad=True)
+    g = torch.randn(B, K * D, L, dtype=torch.float64)
+    out = F.conv1d(z.view(B, K * R, L), w.view(K * D, R, 1), groups=K)
+    out.backward(g)
+    assert rel_err(oracle.dt_proj(z.detach().numpy(), w.detach().numpy()), out.detach().numpy()) < 1e-12
+    dz, dw = oracle.dt_proj_bwd(z.detach().numpy(), w.detach().numpy(), g.numpy())
+    assert rel_err(dz, z.grad.numpy()) < 1e-12
+    assert rel_err(dw, w.grad.numpy()) < 1e-12

@@ -472,3 +472,39 @@ def test_dwconv3x3_rejects_cpu_tensors():
     from xfmamba_b200.conv import dwconv3x3_silu
     with pytest.raises(RuntimeError):
         dwconv3x3_silu(torch.randn(1, 2, 4, 4), torch.randn(2, 1, 3, 3))
+
+
+# ---- low-rank delta projection (reference F.conv1d(dts_r, dt_projs_weight, groups=K), models/fusion_vmamba.py:1155-1157) ----
+@pytest.mark.parametrize("B,K,R,D,L,sliced", [
+    (2, 4, 6, 192, 3136, True), (3, 4, 24, 70, 196, True), (2, 4, 48, 33, 49, True), (2, 2, 64, 40, 256, False),
+    (1, 4, 1, 5, 7, False), (2, 4, 12, 384, 784, True), (1, 4, 8, 16, 1023, False),
+])
+def test_dt_proj_fwd_bwd_vs_oracle(B, K, R, D, L, sliced):
+    from xfmamba_b200.proj import dt_proj
+    rng = np.random.default_rng(B * 1000 + R + L)
+    N = 1
+    full = rng.standard_normal((B, K, R + 2 * N, L)).astype(np.float32)
+    w = (rng.standard_normal((K, D, R)) * R ** -0.5).astype(np.float32)
+    g = rng.standard_normal((B, K * D, L)).astype(np.float32)
+    ft = t(full).requires_grad_()
+    zt = torch.split(ft, [R, N, N], dim=2)[0] if sliced else ft[:, :, :R].contiguous()   # the model passes the split slice as is
+    wt = t(w).requires_grad_()
+    out = dt_proj(zt, wt)
+    assert out.shape == (B, K * D, L)
+    z = full[:, :, :R]
+    assert rel_err(n(out), oracle.dt_proj(z, w)) < TOL32
+    out.backward(t(g))
+    dz, dw = oracle.dt_proj_bwd(z, w, g)
+    assert rel_err(n(ft.grad)[:, :, :R], dz) < TOL32
+    assert np.all(n(ft.grad)[:, :, R:] == 0)
+    assert rel_err(n(wt.grad), dw) < TOL32
+
+
+def test_dt_proj_bf16():
+    from xfmamba_b200.proj import dt_proj
+    torch.manual_seed(2)
+    z = torch.randn(2, 4, 12, 784, device=dev()).bfloat16()
+    w = torch.randn(4, 50, 12, device=dev()) * 12 ** -0.5
+    out = dt_proj(z, w)
+    assert out.dtype == torch.bfloat16
+    assert rel_err(n(out), oracle.dt_proj(n(z), n(w))) < TOL16

@@ -61,6 +61,10 @@ class OracleOps:
         return torch.from_numpy(oracle.dwconv3x3_silu(x.numpy(), weight.detach().numpy(), b, act).astype(np.float32))
 
     @staticmethod
+    def dt_proj(z, weight):
+        return torch.from_numpy(oracle.dt_proj(z.numpy(), weight.detach().numpy()).astype(np.float32))
+
+    @staticmethod
     def swapping_scan(x, x2):
         return torch.from_numpy(oracle.swap_scan(x.numpy(), x2.numpy()))
 
@@ -75,7 +79,7 @@ def test_logits_match_reference_on_cpu_with_oracle_ops(golden, monkeypatch):
     m, sd, g = _mini(golden)
     m.load_state_dict(sd)
     m.eval()
-    for name in ("ss2d_scan", "cross_scan_fn", "selective_scan_fn", "swapping_scan", "swapping_merge", "layer_norm_2d", "dwconv3x3_silu"):
+    for name in ("ss2d_scan", "cross_scan_fn", "selective_scan_fn", "swapping_scan", "swapping_merge", "layer_norm_2d", "dwconv3x3_silu", "dt_proj"):
         monkeypatch.setattr(M.OPS, name, getattr(OracleOps, name))
     with torch.no_grad():
         logits = m(torch.from_numpy(g["xa"]), torch.from_numpy(g["xb"]))
@@ -138,7 +142,7 @@ def test_config1_xfmamba_t_two_pairs_gpu_vs_cpu_oracle_path(monkeypatch):
     with torch.no_grad():
         got = m.to(dev)(xa.to(dev), xb.to(dev)).cpu()
     m = m.cpu()
-    for name in ("ss2d_scan", "cross_scan_fn", "selective_scan_fn", "swapping_scan", "swapping_merge", "layer_norm_2d", "dwconv3x3_silu"):
+    for name in ("ss2d_scan", "cross_scan_fn", "selective_scan_fn", "swapping_scan", "swapping_merge", "layer_norm_2d", "dwconv3x3_silu", "dt_proj"):
         monkeypatch.setattr(M.OPS, name, getattr(OracleOps, name))
     t0 = time.perf_counter()
     with torch.no_grad():

@@ -45,7 +45,7 @@ def test_fused_core_replacement_matches_reference_core(monkeypatch):
     x = torch.randn(2, m.d_inner, 6, 5)
     with torch.no_grad():
         want = m.forward_core(x)
-        for name in ("ss2d_scan", "cross_scan_fn", "layer_norm_2d"):
+        for name in ("ss2d_scan", "cross_scan_fn", "layer_norm_2d", "dt_proj"):
             monkeypatch.setattr(M.OPS, name, getattr(OracleOps, name))
         got = xfpatch._fused_ss2d_core(m, x)
     assert rel_err(got.numpy(), want.numpy()) < 1e-4

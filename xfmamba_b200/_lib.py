@@ -54,7 +54,7 @@ SYMBOLS = [
     "xfs_cross_scan", "xfs_cross_merge", "xfs_swap_scan", "xfs_swap_merge", "xfs_swap_stack",
     "xfs_selective_scan_fwd", "xfs_selective_scan_bwd", "xfs_ss2d_supported", "xfs_ss2d_fwd", "xfs_ss2d_bwd",
     "xfs_layernorm2d_fwd", "xfs_layernorm2d_bwd",
-    "xfs_dwconv3x3_supported", "xfs_dwconv3x3_fwd", "xfs_dwconv3x3_bwd",
+    "xfs_dwconv3x3_supported", "xfs_dwconv3x3_fwd", "xfs_dwconv3x3_bwd", "xfs_dt_proj_fwd",
 ]
 
 
@@ -95,6 +95,7 @@ def lib() -> ctypes.CDLL:
     L.xfs_dwconv3x3_supported.argtypes = [c_i64, c_i64, ctypes.c_int]
     L.xfs_dwconv3x3_fwd.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, ctypes.c_int, ctypes.c_int, c_vp]
     L.xfs_dwconv3x3_bwd.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, ctypes.c_int, ctypes.c_int, c_vp]
+    L.xfs_dt_proj_fwd.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, ctypes.c_int, c_vp]
     _lib = L
     return L
 

@@ -25,6 +25,8 @@ int dwconv_supported(int64_t, int64_t, int);
 int launch_dwconv_fwd(const void*, const float*, const float*, void*, int64_t, int64_t, int64_t, int64_t, int, int, cudaStream_t);
 int launch_dwconv_bwd(const void*, const float*, const float*, const void*, void*, float*, int64_t, int64_t, int64_t, int64_t, int, int, cudaStream_t);
 
+int launch_dtproj_fwd(const void*, const float*, void*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int, cudaStream_t);
+
 static std::atomic<long long> g_launches{0};
 
 int check_launch() {
@@ -186,6 +188,14 @@ int xfs_dwconv3x3_bwd(const void* x, const float* weight, const float* bias, con
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return XFS_ERR_SHAPE;
     if (bad_dtype(dtype)) return XFS_ERR_DTYPE;
     return launch_dwconv_bwd(x, weight, bias, dy, dx, part, B, C, H, W, dtype, act != 0, (cudaStream_t)stream);
+}
+
+int xfs_dt_proj_fwd(const void* z, const float* W, void* delta, int64_t B, int64_t K, int64_t D, int64_t R, int64_t L,
+                    int64_t z_batch_stride, int64_t z_route_stride, int dtype, xfs_stream_t stream) {
+    if (!z || !W || !delta) return XFS_ERR_NULL;
+    if (B <= 0 || K <= 0 || D <= 0 || R <= 0 || L <= 0 || z_batch_stride < 0 || z_route_stride < 0) return XFS_ERR_SHAPE;
+    if (bad_dtype(dtype)) return XFS_ERR_DTYPE;
+    return launch_dtproj_fwd(z, W, delta, B, K, D, R, L, z_batch_stride, z_route_stride, dtype, (cudaStream_t)stream);
 }
 
 }  // extern "C"

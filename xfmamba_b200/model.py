@@ -28,7 +28,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import conv, csm, csms6s, fusion_ops, norm
+from . import conv, csm, csms6s, fusion_ops, norm, proj
 
 OPS = types.SimpleNamespace(
     ss2d_scan=fusion_ops.ss2d_scan,
@@ -38,6 +38,7 @@ OPS = types.SimpleNamespace(
     swapping_merge=fusion_ops.SwappingMerge_multiview.apply,
     layer_norm_2d=norm.layer_norm_2d,
     dwconv3x3_silu=conv.dwconv3x3_silu,
+    dt_proj=proj.dt_proj,
 )
 
 VARIANTS = {   # reference net_fusionmamba.py:151-159
@@ -68,7 +69,7 @@ def ss2d_core(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, Cs_o
     N = A_logs.shape[1]
     L = H * W
     dts_r, Bs, Cs = _route_small(x, x_proj_weight, K, R, N)
-    dts = F.conv1d(dts_r.reshape(B, K * R, L), dt_projs_weight.reshape(K * D, R, 1), groups=K)   # (B, K*D, L)
+    dts = OPS.dt_proj(dts_r, dt_projs_weight)                                # (B, K*D, L)
     As = -A_logs.float().exp()
     Cs_used = Cs if Cs_override is None else Cs_override
     y = OPS.ss2d_scan(x, dts.contiguous(), As, Bs.contiguous(), Cs_used.contiguous(), Ds.float(),
@@ -85,8 +86,8 @@ def shallow_fuse_core(x, x2, x_proj_weight, dt_projs_weight, dt_projs_bias, A_lo
     xs = OPS.swapping_scan(x, x2)                                            # (B, 2, D, L)
     x_dbl = torch.einsum("b k d l, k c d -> b k c l", xs, x_proj_weight)
     dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
-    dts = torch.einsum("b k r l, k d r -> b k d l", dts, dt_projs_weight)
-    ys = OPS.selective_scan_fn(xs.view(B, -1, L), dts.contiguous().view(B, -1, L), -A_logs.float().exp(), Bs.contiguous(),
+    dts = OPS.dt_proj(dts, dt_projs_weight)
+    ys = OPS.selective_scan_fn(xs.view(B, -1, L), dts, -A_logs.float().exp(), Bs.contiguous(),
                                Cs.contiguous(), Ds.float(), dt_projs_bias.reshape(-1).float(), True, True)
     return OPS.swapping_merge(ys.view(B, K, -1, L))
 
