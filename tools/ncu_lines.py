@@ -71,11 +71,18 @@ def main():
     base = int(data[0][0], 16)
     mangled_hint = a.fn or re.sub(r"\W+", ".*", a.kernel)
     maps = sass_line_map(a.so, mangled_hint)
-    # choose the function whose instruction count matches
-    best = None
-    for fn, mp in maps.items():
-        if best is None or abs(len(mp) - len(data)) < abs(len(maps[best]) - len(data)):
-            best = fn
+    # choose the function whose SASS matches the report: same instruction count, then most identical opcodes
+    def score(fn):
+        mp_ = maps[fn]
+        if len(mp_) != len(data):
+            return -abs(len(mp_) - len(data))
+        same = 0
+        for r in data:
+            ent = mp_.get(int(r[0], 16) - base)
+            if ent and ent[1].split()[:2] == r[ix["Source"]].split()[:2]:
+                same += 1
+        return same
+    best = max(maps, key=score)
     mp = maps[best]
     print(f"# kernel: {kname.strip(',')[:120]}\n# sass function: {best} ({len(mp)} instr in cubin, {len(data)} in report)")
     stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
