@@ -24,7 +24,8 @@ def run(B, D, H, W, N, dtype=torch.float32, iters=10):
         if it >= 3: tf += e0.elapsed_time(e1); tb += e1.elapsed_time(e2)
     tf /= iters; tb /= iters
     print(f"B={B:3d} D={D:5d} {H:3d}x{W:<3d} N={N:2d} {str(dtype)[6:]:8s} fwd {tf*1e3:8.1f} us {fb/tf/1e6:7.0f} GB/s | bwd(+memsets) {tb*1e3:8.1f} us {bb/tb/1e6:7.0f} GB/s | elements {B*4*D*L/1e6:7.1f} M  fwd {tf*1e6/(B*4*D*L)*1e3:.2f} ps/el bwd {tb*1e6/(B*4*D*L)*1e3:.2f}")
-for shp in [(64, 192, 56, 56, 1), (64, 256, 56, 56, 1), (64, 512, 28, 28, 1), (64, 1024, 14, 14, 1), (64, 2048, 7, 7, 1), (32, 2048, 7, 7, 16), (8, 256, 128, 128, 1), (8, 1024, 32, 32, 1)]:
+for shp in [(1, 192, 56, 56, 1), (8, 192, 56, 56, 1), (64, 192, 56, 56, 1), (128, 192, 56, 56, 1), (64, 96, 56, 56, 1), (64, 256, 56, 56, 1),
+            (64, 192, 56, 57, 1), (64, 384, 28, 28, 1), (64, 512, 28, 28, 1), (64, 1024, 14, 14, 1), (64, 2048, 7, 7, 1), (32, 2048, 7, 7, 16), (8, 256, 128, 128, 1), (8, 1024, 32, 32, 1)]:
     try: run(*shp)
     except Exception as e: print(shp, "ERR", e)
 run(64, 192, 56, 56, 1, torch.bfloat16)
