@@ -184,8 +184,11 @@ def run_ours(args):
     # reusable output buffers (device-resident leg)
     y = torch.empty((batch, w["D"], L), dtype=torch.float32, device=dev)
     states = torch.empty((batch, 4 * w["D"], _lib.num_chunks(L), w["N"]), dtype=torch.float32, device=dev)
+    # dBs / dCs accumulators: replicated (see xfs_ss2d_bwd_args.acc_replicas), summed over the replicas inside ss2d_bwd_raw
+    n_rep = fusion_ops.ss2d_acc_replicas(w["D"], L)
+    acc_shape = tuple(d["Bs"].shape) if n_rep == 1 else (n_rep,) + tuple(d["Bs"].shape)
     grads = (torch.empty_like(d["x"]), torch.empty_like(d["delta"]), torch.empty_like(d["A"]),
-             torch.empty(d["Bs"].shape, dtype=torch.float32, device=dev), torch.empty(d["Cs"].shape, dtype=torch.float32, device=dev),
+             torch.empty(acc_shape, dtype=torch.float32, device=dev), torch.empty(acc_shape, dtype=torch.float32, device=dev),
              torch.empty_like(d["Ds"]), torch.empty_like(d["delta_bias"]))
     # dA, dDs, ddelta_bias are the parameter gradients.  Two buckets alternate so that the all-reduce of step i (NCCL's own
     # stream) overlaps the kernels of step i+1, as a gradient bucket does with the rest of a backward pass.

@@ -184,6 +184,11 @@ typedef struct {
     float* ddelta_bias;
     int64_t batch, D, N, H, W;
     int32_t dtype, dout_dtype, delta_softplus, scans;
+    /* dBs / dCs receive one contribution per channel and position: all D channels of a batch image add into the same few
+     * L2 lines at the same time, which serialises (measured: 18 % of the config-2 backward, 60 % at 14x14 with D = 1024).
+     * With acc_replicas = R > 1 the accumulators are (R, B, 4, N, L) and channel d adds into replica d % R; the caller sums
+     * over R afterwards (a few MB).  0 or 1: plain (B, 4, N, L). */
+    int32_t acc_replicas, reserved;
 } xfs_ss2d_bwd_args;
 
 XFS_API int xfs_ss2d_supported(int64_t D, int64_t N, int64_t H, int64_t W, int dtype, int backward);

@@ -296,6 +296,8 @@ def test_ss2d_golden_core(xf, golden):
 @pytest.mark.parametrize("shape", [
     (2, 4, 1, 6, 5), (1, 3, 1, 14, 14), (2, 6, 1, 28, 28), (1, 5, 1, 17, 19), (1, 2, 1, 56, 57), (2, 2, 1, 7, 7),
     (1, 2, 4, 7, 7), (2, 3, 16, 7, 7), (1, 2, 3, 16, 17), (1, 1, 1, 1, 300), (1, 2, 1, 32, 8),
+    # one-chunk shapes (64 < L <= 256, L % 4 == 0): the warp-per-channel kernels of csrc/ss2d_mid.cu
+    (2, 5, 1, 14, 14), (1, 4, 1, 16, 16), (2, 3, 1, 9, 8), (1, 2, 1, 10, 20), (1, 6, 1, 12, 11), (3, 1, 1, 4, 17), (1, 9, 1, 13, 20),
 ])
 @pytest.mark.parametrize("model_like", [False, True])
 def test_ss2d_fused_oracle_fp32(xf, shape, model_like):

@@ -45,7 +45,7 @@ class Ss2dBwdArgs(ctypes.Structure):
     _fields_ = [(n, c_vp) for n in ("x", "delta", "A", "Bs", "Cs", "Ds", "delta_bias", "dy", "states", "dx", "ddelta",
                                     "dA", "dBs", "dCs", "dDs", "ddelta_bias")] + \
                [(n, c_i64) for n in ("batch", "D", "N", "H", "W")] + \
-               [(n, c_i32) for n in ("dtype", "dout_dtype", "delta_softplus", "scans")]
+               [(n, c_i32) for n in ("dtype", "dout_dtype", "delta_softplus", "scans", "acc_replicas", "reserved")]
 
 
 # every symbol include/xfscan.h declares (tests/test_cabi.py checks the .so exports all of them)

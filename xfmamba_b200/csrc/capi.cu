@@ -17,6 +17,9 @@ int ss2d_supported(int64_t, int64_t, int64_t, int64_t, int, int);
 int ss2d_small_supported(int64_t, int64_t, int64_t);
 int launch_ss2d_small_fwd(const xfs_ss2d_fwd_args&, cudaStream_t);
 int launch_ss2d_small_bwd(const xfs_ss2d_bwd_args&, cudaStream_t);
+int ss2d_mid_supported(int64_t, int64_t, int64_t);
+int launch_ss2d_mid_fwd(const xfs_ss2d_fwd_args&, cudaStream_t);
+int launch_ss2d_mid_bwd(const xfs_ss2d_bwd_args&, cudaStream_t);
 
 int launch_ln2d_fwd(const void*, const float*, const float*, void*, float*, float*, int64_t, int64_t, int64_t, float, int, cudaStream_t);
 int launch_ln2d_bwd(const void*, const void*, const float*, const float*, const float*, void*, float*, float*, int64_t, int64_t, int64_t, int, cudaStream_t);
@@ -139,6 +142,10 @@ int xfs_ss2d_fwd(const xfs_ss2d_fwd_args* a, xfs_stream_t stream) {
     if (bad_dtype(a->dtype) || (a->out_dtype != XFS_F32 && a->out_dtype != a->dtype)) return XFS_ERR_DTYPE;
     if (a->scans != XFS_SCANS_CROSS2D) return XFS_ERR_UNSUPPORTED;
     if (ss2d_small_supported(a->N, a->H, a->W)) return launch_ss2d_small_fwd(*a, (cudaStream_t)stream);   // L <= 64
+    if (ss2d_mid_supported(a->N, a->H, a->W)) {                    // one chunk, N = 1, fp32, aligned: warp-per-channel kernel
+        const int rc = launch_ss2d_mid_fwd(*a, (cudaStream_t)stream);
+        if (rc != XFS_ERR_UNSUPPORTED) return rc;
+    }
     if (!ss2d_supported(a->D, a->N, a->H, a->W, a->dtype, 0)) return XFS_ERR_UNSUPPORTED;
     return launch_ss2d_fwd(*a, (cudaStream_t)stream);
 }
@@ -151,7 +158,12 @@ int xfs_ss2d_bwd(const xfs_ss2d_bwd_args* a, xfs_stream_t stream) {
     if (a->batch <= 0 || a->D <= 0 || a->N <= 0 || a->H <= 0 || a->W <= 0) return XFS_ERR_SHAPE;
     if (bad_dtype(a->dtype) || (a->dout_dtype != XFS_F32 && a->dout_dtype != a->dtype)) return XFS_ERR_DTYPE;
     if (a->scans != XFS_SCANS_CROSS2D) return XFS_ERR_UNSUPPORTED;
-    if (ss2d_small_supported(a->N, a->H, a->W)) return launch_ss2d_small_bwd(*a, (cudaStream_t)stream);   // L <= 64
+    if (a->acc_replicas < 0 || a->acc_replicas > 64) return XFS_ERR_SHAPE;
+    if (ss2d_small_supported(a->N, a->H, a->W)) return launch_ss2d_small_bwd(*a, (cudaStream_t)stream);   // L <= 64 (replica 0 only)
+    if (ss2d_mid_supported(a->N, a->H, a->W)) {                    // one chunk, N = 1, fp32, aligned: warp-per-channel kernel
+        const int rc = launch_ss2d_mid_bwd(*a, (cudaStream_t)stream);
+        if (rc != XFS_ERR_UNSUPPORTED) return rc;
+    }
     if (!ss2d_supported(a->D, a->N, a->H, a->W, a->dtype, 1)) return XFS_ERR_UNSUPPORTED;
     return launch_ss2d_bwd(*a, (cudaStream_t)stream);
 }

@@ -53,8 +53,9 @@ ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
     T* __restrict__ ddelta = reinterpret_cast<T*>(p.ddelta);
     const T* __restrict__ Bk = reinterpret_cast<const T*>(p.Bs) + ((int64_t)b * 4 + k) * N * L;
     const T* __restrict__ Ck = reinterpret_cast<const T*>(p.Cs) + ((int64_t)b * 4 + k) * N * L;
-    float* __restrict__ dBk = p.dBs + ((int64_t)b * 4 + k) * N * L;
-    float* __restrict__ dCk = p.dCs + ((int64_t)b * 4 + k) * N * L;
+    const int rep = p.acc_replicas > 1 ? d0 % p.acc_replicas : 0;      // accumulator replica of this channel (see xfscan.h)
+    float* __restrict__ dBk = p.dBs + (((int64_t)rep * p.batch + b) * 4 + k) * N * L;
+    float* __restrict__ dCk = p.dCs + (((int64_t)rep * p.batch + b) * 4 + k) * N * L;
     const bool vin = kFast || (row_vec_ok(delta, L) && row_vec_ok(reinterpret_cast<const T*>(p.Bs), L) &&
                                row_vec_ok(reinterpret_cast<const T*>(p.Cs), L));
     const bool vout = kFast || row_vec_ok(ddelta, L);

@@ -1,0 +1,387 @@
+// ss2d_mid.cu -- fused SS2D forward / backward for sequences that fit ONE chunk: 64 < L = H*W <= 256, N = 1, fp32.
+//
+// XFMamba's third backbone stage (14x14 tokens, 8 or 15 of the 14 / 21 blocks) lives here, and 16x16 at 512^2 input.  In
+// the general kernels a CTA is four route-warps around four shared image buffers; with a single chunk per route all of
+// that CTA's fixed work (block staging loops, three barriers, the merge loop) is paid for 196 positions, and ncu shows
+// ~95 issued instructions per (b, k, d, l) against 43 at 56x56, 20 % of the stall samples at barriers.
+//
+// Here ONE WARP owns a channel image and runs its four routes back to back:
+//   * lane i holds spatial positions 8i .. 8i+7 in registers -- that IS the scan order of routes 0 / 2 (the flip only
+//     reverses the lane order of the warp scan), and the column-major copy for routes 1 / 3 is one round trip through a
+//     1 KB per-warp shared-memory tile (__syncwarp only, no CTA barrier anywhere);
+//   * y of routes 0+2 and of routes 1+3 accumulate in registers, one transposition back at the end;
+//   * the four routes are straight-line code, so the compiler overlaps the loads and the element-wise phase of route k+1
+//     with the shuffle latency of route k.
+// Backward: same structure, x and dy held in both orders, du accumulated in registers, no checkpoints needed (h starts at 0).
+#include <initializer_list>
+
+#include "ss2d_fused.cuh"
+
+namespace xfs {
+
+constexpr int kMidWarps = 4;
+constexpr int kMidTile = 256 + 8;        // floats per warp tile
+
+struct MidLane {
+    int p0;            // first position held by this lane
+    int g0f, g1f;      // granule offsets for forward-ordered rows (clamped to 0 when outside the row)
+    int g0r, g1r;      // granule offsets for flipped rows: scan index L - 8 - p0
+    bool ok0, ok1;     // granule p0..p0+3 / p0+4..p0+7 inside the image
+};
+
+__device__ __forceinline__ MidLane mid_lane(int lane, int L) {
+    MidLane m;
+    m.p0 = lane * 8;
+    m.ok0 = m.p0 + 4 <= L; m.ok1 = m.p0 + 8 <= L;
+    m.g0f = m.ok0 ? m.p0 : 0; m.g1f = m.ok1 ? m.p0 + 4 : 0;
+    const int l0 = L - 8 - m.p0;           // lowest address of the flipped range; its HIGH granule maps to positions p0..p0+3
+    m.g0r = (l0 >= 0) ? l0 : 0;            // granule [l0, l0+4)   <-> positions p0+4 .. p0+7 (valid iff ok1)
+    m.g1r = (l0 + 4 >= 0 && m.ok0) ? l0 + 4 : 0;
+    return m;
+}
+
+// For the 8 consecutive indices q0 .. q0+7 of an (R rows x C columns) image stored with rows of length C, the index of
+// the same element in the transposed storage (rows of length R): (r, c) -> c * R + r.  One division, then increments.
+// Indices >= L (lanes past the image) map to themselves, i.e. into the zero-filled tail of the tile.
+__device__ __forceinline__ void mid_transposed_index(int q0, int R, int C, int L, int (&out)[8]) {
+    int r = q0 / C, c = q0 - r * C;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        out[i] = (q0 + i < L) ? c * R + r : q0 + i;
+        if (++c == C) { c = 0; ++r; }
+    }
+}
+
+// values held in row-major position order (lane i: 8i..8i+7) -> the same image in column-major position order
+__device__ __forceinline__ void mid_transpose(float* tile, const float (&src)[8], float (&dst)[8], const int (&gather)[8], int p0) {
+    __syncwarp();
+    *reinterpret_cast<float4*>(tile + p0) = make_float4(src[0], src[1], src[2], src[3]);
+    *reinterpret_cast<float4*>(tile + p0 + 4) = make_float4(src[4], src[5], src[6], src[7]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dst[i] = tile[gather[i]];
+}
+
+// delta / B / C of one route in ADDRESS order plus its three parameters, exactly as loaded.  The loads of route k+1 are
+// issued (in program order) BEFORE route k is computed: each warp then pays one exposed memory round trip, not four.
+struct MidLoads {
+    float dt[8], B[8], C[8];
+    float bias, Dd, A;
+};
+
+template <bool kRev>
+__device__ __forceinline__ void mid_issue(MidLoads& r, const float* __restrict__ dt_row, const float* __restrict__ Brow,
+                                          const float* __restrict__ Crow, const float* __restrict__ A, const float* __restrict__ Ds,
+                                          const float* __restrict__ dbias, int kd, const MidLane& m) {
+    const int g0 = kRev ? m.g0r : m.g0f, g1 = kRev ? m.g1r : m.g1f;
+    load8_at<float>(dt_row, g0, g1, r.dt);
+    load8_at<float>(Brow, g0, g1, r.B);
+    load8_at<float>(Crow, g0, g1, r.C);
+    r.bias = dbias ? __ldg(dbias + kd) : 0.0f;
+    r.Dd = Ds ? __ldg(Ds + kd) : 0.0f;
+    r.A = __ldg(A + kd);
+}
+
+// ---- one route of the forward, everything in registers ----------------------------------------------------------------
+template <bool kRev>
+__device__ __forceinline__ void mid_route_fwd(const xfs_ss2d_fwd_args& p, const MidLoads& r, const MidLane& m, int L, int lane,
+                                              const float (&u)[8], float (&yacc)[8], float* __restrict__ state_out) {
+    const float bias = r.bias, Dd = r.Dd, A2 = r.A * kLog2e;
+    const float (&dta)[8] = r.dt;
+    const float (&Ba)[8] = r.B;
+    const float (&Ca)[8] = r.C;
+    float dtp[8], Bp[8], Cp[8];
+    to_pos<kRev>(dta, dtp); to_pos<kRev>(Ba, Bp); to_pos<kRev>(Ca, Cp);
+    // positions >= L must be identity maps (they come first in a flipped route); softplus(-inf) = 0, (-bias) + bias = 0
+    const float off = p.delta_softplus ? -INFINITY : -bias;
+    if (kRev) {      // a forward route meets them after every real position: nothing to do there
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (m.p0 + i >= L) dtp[i] = off;
+    }
+    f2 dt2[4], u2[4], B2[4], C2[4], a2[4], bu2[4], S2[4], P2[4];
+    pack8(dtp, dt2); pack8(u, u2); pack8(Bp, B2); pack8(Cp, C2);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const f2 xx = add2(dt2[j], splat2(bias));
+        f2 e;
+        dt2[j] = p.delta_softplus ? softplus2(xx, e) : xx;
+        a2[j] = ex2_2(mul2(dt2[j], splat2(A2)));
+        bu2[j] = mul2(dt2[j], mul2(B2[j], u2[j]));
+    }
+    float Pr = 1.0f, Sr = 0.0f;
+    if (!kRev) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            Sr = fmaf(a2[j].x, Sr, bu2[j].x); Pr *= a2[j].x; S2[j].x = Sr; P2[j].x = Pr;
+            Sr = fmaf(a2[j].y, Sr, bu2[j].y); Pr *= a2[j].y; S2[j].y = Sr; P2[j].y = Pr;
+        }
+    } else {
+#pragma unroll
+        for (int j = 3; j >= 0; --j) {
+            Sr = fmaf(a2[j].y, Sr, bu2[j].y); Pr *= a2[j].y; S2[j].y = Sr; P2[j].y = Pr;
+            Sr = fmaf(a2[j].x, Sr, bu2[j].x); Pr *= a2[j].x; S2[j].x = Sr; P2[j].x = Pr;
+        }
+    }
+    float h_out;
+    const float h_in = warp_prefix<kRev>(Pr, Sr, 0.0f, lane, h_out);
+    if (state_out && lane == 0) *state_out = h_out;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const f2 h2 = fma2(P2[j], splat2(h_in), S2[j]);
+        const f2 y2 = fma2(C2[j], h2, mul2(splat2(Dd), u2[j]));
+        yacc[2 * j] += y2.x; yacc[2 * j + 1] += y2.y;
+    }
+}
+
+__global__ void __launch_bounds__(kMidWarps * 32, 4)
+ss2d_mid_fwd_kernel(const xfs_ss2d_fwd_args p) {
+    __shared__ __align__(16) float tiles[kMidWarps][kMidTile];
+    const int H = (int)p.H, W = (int)p.W, L = H * W, D = (int)p.D;
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const int64_t chan = (int64_t)blockIdx.x * kMidWarps + wp;
+    if (chan >= p.batch * D) return;                 // warps are independent: no CTA barrier below
+    const int b = (int)(chan / D), d = (int)(chan - (int64_t)b * D);
+    float* tile = tiles[wp];
+    const MidLane m = mid_lane(lane, L);
+
+    const float* __restrict__ xrow = reinterpret_cast<const float*>(p.x) + chan * L;
+    const float* __restrict__ delta = reinterpret_cast<const float*>(p.delta) + (int64_t)b * 4 * D * L;
+    const float* __restrict__ Bs = reinterpret_cast<const float*>(p.Bs) + (int64_t)b * 4 * L;
+    const float* __restrict__ Cs = reinterpret_cast<const float*>(p.Cs) + (int64_t)b * 4 * L;
+    float* st = p.states ? p.states + (int64_t)b * 4 * D : nullptr;       // (B, 4D, 1, 1)
+#define XFS_MID_ISSUE(R, K, REV)                                                                                                      \
+    mid_issue<REV>(R, delta + (int64_t)((K) * D + d) * L, Bs + (K) * L, Cs + (K) * L, p.A, p.Ds, p.delta_bias, (K) * D + d, m)
+    // every load the first two routes need is issued before the first loaded value is touched (in-order issue: the warp
+    // stalls at the first use, and whatever has not been issued by then waits behind it)
+    MidLoads ra, rb;
+    float u[8], uT[8];
+    XFS_MID_ISSUE(ra, 0, false);
+    load8_at<float>(xrow, m.g0f, m.g1f, u);
+    XFS_MID_ISSUE(rb, 2, true);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (m.p0 + i >= L) u[i] = 0.0f;
+    float yN[8], yT[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { yN[i] = 0.0f; yT[i] = 0.0f; }
+    int gat[8];                                      // spatial index of column-major positions p0 .. p0+7 (q = w*H + h -> h*W + w)
+    mid_transposed_index(m.p0, W, H, L, gat);
+    mid_transpose(tile, u, uT, gat, m.p0);
+    // accumulation order of the reference merge: (y0 + y2) + (y1 + y3)
+    mid_route_fwd<false>(p, ra, m, L, lane, u, yN, st ? st + 0 * D + d : nullptr);
+    XFS_MID_ISSUE(ra, 1, false);
+    mid_route_fwd<true>(p, rb, m, L, lane, u, yN, st ? st + 2 * D + d : nullptr);
+    XFS_MID_ISSUE(rb, 3, true);
+    mid_route_fwd<false>(p, ra, m, L, lane, uT, yT, st ? st + 1 * D + d : nullptr);
+    mid_route_fwd<true>(p, rb, m, L, lane, uT, yT, st ? st + 3 * D + d : nullptr);
+#undef XFS_MID_ISSUE
+
+    // y[p] = yN[p] + yT[column-major index of p]
+    int sc[8];                                       // column-major index of spatial positions p0 .. p0+7
+    mid_transposed_index(m.p0, H, W, L, sc);
+    float back[8];
+    mid_transpose(tile, yT, back, sc, m.p0);
+    float* __restrict__ yrow = reinterpret_cast<float*>(p.y) + chan * L;
+    if (m.ok0) *reinterpret_cast<float4*>(yrow + m.p0) = make_float4(yN[0] + back[0], yN[1] + back[1], yN[2] + back[2], yN[3] + back[3]);
+    if (m.ok1) *reinterpret_cast<float4*>(yrow + m.p0 + 4) = make_float4(yN[4] + back[4], yN[5] + back[5], yN[6] + back[6], yN[7] + back[7]);
+}
+
+
+// ---- one route of the backward ------------------------------------------------------------------------------------------
+// u, dy: this route's position order (row-major for routes 0/2, column-major for 1/3); du accumulates in the same order.
+template <bool kRev>
+__device__ __forceinline__ void mid_route_bwd(const xfs_ss2d_bwd_args& p, const MidLoads& r, float* __restrict__ ddt_row,
+                                              float* __restrict__ dBrow, float* __restrict__ dCrow, const MidLane& m, int L, int lane,
+                                              const float (&u)[8], const float (&dy)[8], float (&du)[8], float (&pg)[3]) {
+    const int g0 = kRev ? m.g0r : m.g0f, g1 = kRev ? m.g1r : m.g1f;
+    const float bias = r.bias, Dd = r.Dd, An = r.A, A2 = An * kLog2e;
+    const float (&dta)[8] = r.dt;
+    const float (&Ba)[8] = r.B;
+    const float (&Ca)[8] = r.C;
+    float dtp[8], Bp[8], Cp[8];
+    to_pos<kRev>(dta, dtp); to_pos<kRev>(Ba, Bp); to_pos<kRev>(Ca, Cp);
+    const float off = p.delta_softplus ? -INFINITY : -bias;      // positions >= L: dt = 0 makes every term below exactly 0
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (m.p0 + i >= L) dtp[i] = off;
+    f2 x2[4], u2[4], dy2[4], B2[4], C2[4], dt2[4], sig2[4], a2[4], bu2[4], Bu2[4], cd2[4];
+    pack8(dtp, x2); pack8(u, u2); pack8(dy, dy2); pack8(Bp, B2); pack8(Cp, C2);
+    f2 dD2 = splat2(0.0f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const f2 xx = add2(x2[j], splat2(bias));
+        f2 e = splat2(0.0f);
+        dt2[j] = p.delta_softplus ? softplus2(xx, e) : xx;
+        const f2 w = add2(e, splat2(1.0f));
+        f2 sg = mul2(e, make_float2(rcp(w.x), rcp(w.y)));       // sigmoid(x) = e / (1 + e); x > 20: softplus is the identity
+        sg.x = (xx.x > 20.0f) ? 1.0f : sg.x;
+        sg.y = (xx.y > 20.0f) ? 1.0f : sg.y;
+        sig2[j] = p.delta_softplus ? sg : splat2(1.0f);
+        Bu2[j] = mul2(B2[j], u2[j]);
+        cd2[j] = mul2(C2[j], dy2[j]);
+        a2[j] = ex2_2(mul2(dt2[j], splat2(A2)));
+        bu2[j] = mul2(dt2[j], Bu2[j]);
+        dD2 = fma2(dy2[j], u2[j], dD2);
+    }
+    float a[8], bu[8], cd[8], S[8], P[8], Sq[8], Pq[8];
+    unpack8(a2, a); unpack8(bu2, bu); unpack8(cd2, cd);
+    float Pr = 1.0f, Sr = 0.0f, Pqr = 1.0f, Sqr = 0.0f;
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) {           // forward re-scan, walk order
+        const int i = kRev ? 7 - ii : ii;
+        Sr = fmaf(a[i], Sr, bu[i]); Pr *= a[i]; S[i] = Sr; P[i] = Pr;
+    }
+#pragma unroll
+    for (int ii = 0; ii < 8; ++ii) {           // adjoint scan, opposite order
+        const int i = kRev ? ii : 7 - ii;
+        Sqr = a[i] * (cd[i] + Sqr); Pqr *= a[i]; Sq[i] = Sqr; Pq[i] = Pqr;
+    }
+    float h_in, q_in, q_out;
+    warp_prefix_dual<kRev>(Pr, Sr, 0.0f, Pqr, Sqr, 0.0f, lane, h_in, q_in, q_out);
+    float q[8], gi[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = fmaf(Pq[i], q_in, Sq[i]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {              // g_i = C_i dy_i + q of the element that FOLLOWS i in the forward walk
+        const float qn = kRev ? (i == 0 ? q_in : q[i == 0 ? 0 : i - 1]) : (i == 7 ? q_in : q[i == 7 ? 7 : i + 1]);
+        gi[i] = cd[i] + qn;
+    }
+    f2 S2[4], P2[4], gi2[4], dB2[4], dC2[4], ddt2[4];
+    pack8(S, S2); pack8(P, P2); pack8(gi, gi2);
+    f2 dA2 = splat2(0.0f), dbias2 = splat2(0.0f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const f2 h2 = fma2(P2[j], splat2(h_in), S2[j]);
+        const f2 hp2 = fma2(bu2[j], splat2(-1.0f), h2);         // a_i * h_{i-1}
+        const f2 gdt2 = mul2(gi2[j], dt2[j]);
+        const f2 du2 = fma2(gdt2, B2[j], mul2(splat2(Dd), dy2[j]));
+        du[2 * j] += du2.x; du[2 * j + 1] += du2.y;
+        ddt2[j] = mul2(mul2(gi2[j], fma2(splat2(An), hp2, Bu2[j])), sig2[j]);
+        dbias2 = add2(dbias2, ddt2[j]);
+        dA2 = fma2(gdt2, hp2, dA2);
+        dB2[j] = mul2(gdt2, u2[j]);
+        dC2[j] = mul2(dy2[j], h2);
+    }
+    // ddelta, dB, dC back in address order of this route's rows
+    float v[8], va[8];
+    unpack8(ddt2, v); to_pos<kRev>(v, va);
+    const bool okA = kRev ? m.ok1 : m.ok0, okB = kRev ? m.ok0 : m.ok1;      // validity of the low / high ADDRESS granule
+    if (okA) *reinterpret_cast<float4*>(ddt_row + g0) = make_float4(va[0], va[1], va[2], va[3]);
+    if (okB) *reinterpret_cast<float4*>(ddt_row + g1) = make_float4(va[4], va[5], va[6], va[7]);
+    unpack8(dB2, v); to_pos<kRev>(v, va);
+    if (okA) red_add_v4_relaxed(dBrow + g0, va[0], va[1], va[2], va[3]);
+    if (okB) red_add_v4_relaxed(dBrow + g1, va[4], va[5], va[6], va[7]);
+    unpack8(dC2, v); to_pos<kRev>(v, va);
+    if (okA) red_add_v4_relaxed(dCrow + g0, va[0], va[1], va[2], va[3]);
+    if (okB) red_add_v4_relaxed(dCrow + g1, va[4], va[5], va[6], va[7]);
+    // parameter gradients of this (route, channel): per-lane partial sums, reduced and added once at the end of the kernel
+    pg[0] = dA2.x + dA2.y; pg[1] = dD2.x + dD2.y; pg[2] = dbias2.x + dbias2.y;
+}
+
+__global__ void __launch_bounds__(kMidWarps * 32, 3)
+ss2d_mid_bwd_kernel(const xfs_ss2d_bwd_args p) {
+    __shared__ __align__(16) float tiles[kMidWarps][kMidTile];
+    const int H = (int)p.H, W = (int)p.W, L = H * W, D = (int)p.D;
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const int64_t chan = (int64_t)blockIdx.x * kMidWarps + wp;
+    if (chan >= p.batch * D) return;
+    const int b = (int)(chan / D), d = (int)(chan - (int64_t)b * D);
+    float* tile = tiles[wp];
+    const MidLane m = mid_lane(lane, L);
+
+    const float* __restrict__ delta = reinterpret_cast<const float*>(p.delta) + (int64_t)b * 4 * D * L;
+    float* __restrict__ ddelta = reinterpret_cast<float*>(p.ddelta) + (int64_t)b * 4 * D * L;
+    const float* __restrict__ Bs = reinterpret_cast<const float*>(p.Bs) + (int64_t)b * 4 * L;
+    const float* __restrict__ Cs = reinterpret_cast<const float*>(p.Cs) + (int64_t)b * 4 * L;
+    const int rep = p.acc_replicas > 1 ? d % p.acc_replicas : 0;        // accumulator replica of this channel (see xfscan.h)
+    float* __restrict__ dBs = p.dBs + ((int64_t)rep * p.batch + b) * 4 * L;
+    float* __restrict__ dCs = p.dCs + ((int64_t)rep * p.batch + b) * 4 * L;
+#define XFS_MID_ISSUE(R, K, REV)                                                                                                      \
+    mid_issue<REV>(R, delta + (int64_t)((K) * D + d) * L, Bs + (K) * L, Cs + (K) * L, p.A, p.Ds, p.delta_bias, (K) * D + d, m)
+#define XFS_MID_ROUTE(R, K, REV, U, DY, DU)                                                                                           \
+    mid_route_bwd<REV>(p, R, ddelta + (int64_t)((K) * D + d) * L, dBs + (K) * L, dCs + (K) * L, m, L, lane, U, DY, DU, pg[K])
+    MidLoads ra, rb;
+    float u[8], dy[8], duN[8], pg[4][3];
+    XFS_MID_ISSUE(ra, 0, false);         // everything routes 0 and 2 need, issued before the first use (see the forward)
+    load8_at<float>(reinterpret_cast<const float*>(p.x) + chan * L, m.g0f, m.g1f, u);
+    load8_at<float>(reinterpret_cast<const float*>(p.dy) + chan * L, m.g0f, m.g1f, dy);
+    XFS_MID_ISSUE(rb, 2, true);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        duN[i] = 0.0f;
+        if (m.p0 + i >= L) { u[i] = 0.0f; dy[i] = 0.0f; }
+    }
+    XFS_MID_ROUTE(ra, 0, false, u, dy, duN);
+    XFS_MID_ISSUE(ra, 1, false);
+    XFS_MID_ROUTE(rb, 2, true, u, dy, duN);
+    // the row-major copies are done: turn them into the column-major ones for routes 1 / 3
+    float uT[8], dyT[8], duT[8];
+    {
+        int gat[8];
+        mid_transposed_index(m.p0, W, H, L, gat);
+        mid_transpose(tile, u, uT, gat, m.p0);
+        mid_transpose(tile, dy, dyT, gat, m.p0);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) duT[i] = 0.0f;
+    XFS_MID_ISSUE(rb, 3, true);
+    XFS_MID_ROUTE(ra, 1, false, uT, dyT, duT);
+    XFS_MID_ROUTE(rb, 3, true, uT, dyT, duT);
+#undef XFS_MID_ROUTE
+#undef XFS_MID_ISSUE
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int t = 0; t < 3; ++t) pg[k][t] += __shfl_xor_sync(kFull, pg[k][t], o);
+    if (lane < 4) {                        // lane k adds the sums of route k
+        const int kd = lane * D + d;
+        const float sA = lane == 0 ? pg[0][0] : lane == 1 ? pg[1][0] : lane == 2 ? pg[2][0] : pg[3][0];
+        const float sD = lane == 0 ? pg[0][1] : lane == 1 ? pg[1][1] : lane == 2 ? pg[2][1] : pg[3][1];
+        const float sb = lane == 0 ? pg[0][2] : lane == 1 ? pg[1][2] : lane == 2 ? pg[2][2] : pg[3][2];
+        atomicAdd(p.dA + kd, sA);
+        if (p.dDs) atomicAdd(p.dDs + kd, sD);
+        if (p.ddelta_bias) atomicAdd(p.ddelta_bias + kd, sb);
+    }
+    int sc[8];
+    mid_transposed_index(m.p0, H, W, L, sc);
+    float back[8];
+    mid_transpose(tile, duT, back, sc, m.p0);
+    float* __restrict__ dxrow = reinterpret_cast<float*>(p.dx) + chan * L;
+    if (m.ok0) *reinterpret_cast<float4*>(dxrow + m.p0) = make_float4(duN[0] + back[0], duN[1] + back[1], duN[2] + back[2], duN[3] + back[3]);
+    if (m.ok1) *reinterpret_cast<float4*>(dxrow + m.p0 + 4) = make_float4(duN[4] + back[4], duN[5] + back[5], duN[6] + back[6], duN[7] + back[7]);
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------
+int ss2d_mid_supported(int64_t N, int64_t H, int64_t W) {
+    const int64_t L = H * W;
+    return N == 1 && L > kSmallL && L <= kChunk && (L % 4 == 0);
+}
+
+static bool mid_ptrs_ok(std::initializer_list<const void*> ps) {
+    for (const void* q : ps)
+        if (q && !aligned16(q)) return false;
+    return true;
+}
+
+// returns XFS_ERR_UNSUPPORTED when the dtype / alignment preconditions do not hold (the caller then takes the general kernels)
+int launch_ss2d_mid_fwd(const xfs_ss2d_fwd_args& a, cudaStream_t st) {
+    if (a.dtype != XFS_F32 || a.out_dtype != XFS_F32 || !mid_ptrs_ok({a.x, a.delta, a.Bs, a.Cs, a.y})) return XFS_ERR_UNSUPPORTED;
+    const int64_t chans = a.batch * a.D;
+    const unsigned grid = (unsigned)((chans + kMidWarps - 1) / kMidWarps);
+    ss2d_mid_fwd_kernel<<<grid, kMidWarps * 32, 0, st>>>(a);
+    return check_launch();
+}
+
+int launch_ss2d_mid_bwd(const xfs_ss2d_bwd_args& a, cudaStream_t st) {
+    if (a.dtype != XFS_F32 || a.dout_dtype != XFS_F32 || !mid_ptrs_ok({a.x, a.delta, a.Bs, a.Cs, a.dy, a.dx, a.ddelta, a.dBs, a.dCs}))
+        return XFS_ERR_UNSUPPORTED;
+    const int64_t chans = a.batch * a.D;
+    const unsigned grid = (unsigned)((chans + kMidWarps - 1) / kMidWarps);
+    ss2d_mid_bwd_kernel<<<grid, kMidWarps * 32, 0, st>>>(a);
+    return check_launch();
+}
+
+}  // namespace xfs

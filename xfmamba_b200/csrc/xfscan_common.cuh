@@ -274,6 +274,12 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// same reduction WITHOUT the compiler-level memory fence: for accumulators this kernel never reads back, so that loads of
+// later, independent work may be scheduled across it (ss2d_mid.cu runs four routes as straight-line code)
+__device__ __forceinline__ void red_add_v4_relaxed(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);

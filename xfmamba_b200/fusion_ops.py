@@ -12,6 +12,8 @@
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -19,7 +21,7 @@ from .csm import cross_merge_raw, cross_scan_raw
 from .csms6s import _check_scan_args, selective_scan_bwd_raw, selective_scan_fwd_raw
 
 __all__ = ["SwappingScan_multiview", "SwappingMerge_multiview", "swapping_scan", "swapping_merge", "ss2d_scan",
-           "SS2DScanFn", "ss2d_fused_supported", "ss2d_fwd_raw", "ss2d_bwd_raw"]
+           "SS2DScanFn", "ss2d_fused_supported", "ss2d_fwd_raw", "ss2d_bwd_raw", "ss2d_acc_replicas"]
 
 
 def _swap_call(fn_name, a, b, outs, B, C, L, dev):
@@ -140,18 +142,38 @@ def ss2d_fwd_raw(x, delta, A, Bs, Cs, Ds, delta_bias, delta_softplus=True, out_d
     return y, states
 
 
+def ss2d_acc_replicas(D, L):
+    """Replicas of the dBs/dCs accumulators (``xfs_ss2d_bwd_args.acc_replicas``): every channel of a batch image adds into
+    the same L2 lines at the same time; spreading the D channels over R copies removes that serialisation."""
+    if L <= 64:
+        return 1                      # the short-sequence kernel already sums a CTA's channels in shared memory
+    env = os.environ.get("XFS_ACC_REPLICAS")
+    if env:
+        return max(1, min(int(env), int(D), 64))
+    # measured on B200 (profiles/r01_shape_sweep.md): 4 copies recover most of the loss at 56x56 (more copies cost more in
+    # zero-fills and in the final sum than they save), short rows with many channels want 8-16
+    R = 4 if L >= 2048 else (8 if D < 1024 else 16)
+    return max(1, min(R, int(D)))
+
+
 def ss2d_bwd_raw(x, delta, A, Bs, Cs, Ds, delta_bias, dy, states, delta_softplus=True, out=None, zero=True):
     """One launch of the fused backward kernel (C ABI ``xfs_ss2d_bwd``).  Returns (dx, ddelta, dA, dBs, dCs, dDs,
-    ddelta_bias) with dBs/dCs as the fp32 accumulators.  ``out`` may carry those 7 buffers for reuse; the accumulated
-    ones are zero-filled here (stream-ordered memsets) unless ``zero=False`` (caller already did), as the reference host
-    code does (selective_scan.cpp:331-337)."""
+    ddelta_bias) with dBs/dCs fp32.  ``out`` may carry the 7 buffers for reuse; its dBs/dCs entries may be replicated
+    accumulators (R, B, 4, N, L) (see ``ss2d_acc_replicas``), which are summed over R here.  The accumulated buffers are
+    zero-filled here (stream-ordered memsets) unless ``zero=False`` (caller already did), as the reference host code does
+    (selective_scan.cpp:331-337)."""
     Bsz, D, H, W = x.shape
     N, dev = Bs.shape[2], x.device
     if out is None:
+        R = ss2d_acc_replicas(D, H * W)
+        acc_shape = tuple(Bs.shape) if R == 1 else (R,) + tuple(Bs.shape)
         out = (torch.empty_like(x), torch.empty_like(delta), torch.empty_like(A),
-               torch.empty(Bs.shape, dtype=torch.float32, device=dev), torch.empty(Cs.shape, dtype=torch.float32, device=dev),
+               torch.empty(acc_shape, dtype=torch.float32, device=dev), torch.empty(acc_shape, dtype=torch.float32, device=dev),
                None if Ds is None else torch.empty_like(Ds), None if delta_bias is None else torch.empty_like(delta_bias))
     dx, ddelta, dA, dBs, dCs, dDs, dbias = out
+    R = dBs.shape[0] if dBs.dim() == 5 else 1
+    if dCs.dim() != dBs.dim() or (dCs.dim() == 5 and dCs.shape[0] != R):
+        raise RuntimeError("ss2d_bwd_raw: dBs and dCs accumulators must have the same number of replicas")
     if zero:
         for acc in (dA, dBs, dCs, dDs, dbias):
             if acc is not None:
@@ -160,10 +182,12 @@ def ss2d_bwd_raw(x, delta, A, Bs, Cs, Ds, delta_bias, dy, states, delta_softplus
         args = _lib.Ss2dBwdArgs(_lib.ptr(x), _lib.ptr(delta), _lib.ptr(A), _lib.ptr(Bs), _lib.ptr(Cs), _lib.ptr(Ds),
                                 _lib.ptr(delta_bias), _lib.ptr(dy), _lib.ptr(states), _lib.ptr(dx), _lib.ptr(ddelta),
                                 _lib.ptr(dA), _lib.ptr(dBs), _lib.ptr(dCs), _lib.ptr(dDs), _lib.ptr(dbias),
-                                Bsz, D, N, H, W, _lib.dtype_code(x), _lib.dtype_code(dy), int(bool(delta_softplus)), 0)
+                                Bsz, D, N, H, W, _lib.dtype_code(x), _lib.dtype_code(dy), int(bool(delta_softplus)), 0, R, 0)
         with torch.cuda.device(dev):
             rc = _lib.lib().xfs_ss2d_bwd(args, _lib.stream(dev))
         _lib.check(rc, "ss2d_bwd")
+    if dBs.dim() == 5:
+        dBs, dCs = dBs.sum(0), dCs.sum(0)
     return dx, ddelta, dA, dBs, dCs, dDs, dbias
 
 
