@@ -159,7 +159,7 @@ int xfs_ss2d_bwd(const xfs_ss2d_bwd_args* a, xfs_stream_t stream) {
     if (bad_dtype(a->dtype) || (a->dout_dtype != XFS_F32 && a->dout_dtype != a->dtype)) return XFS_ERR_DTYPE;
     if (a->scans != XFS_SCANS_CROSS2D) return XFS_ERR_UNSUPPORTED;
     if (a->acc_replicas < 0 || a->acc_replicas > 64) return XFS_ERR_SHAPE;
-    if (ss2d_small_supported(a->N, a->H, a->W)) return launch_ss2d_small_bwd(*a, (cudaStream_t)stream);   // L <= 64 (replica 0 only)
+    if (ss2d_small_supported(a->N, a->H, a->W)) return launch_ss2d_small_bwd(*a, (cudaStream_t)stream);   // L <= 64
     if (ss2d_mid_supported(a->N, a->H, a->W)) {                    // one chunk, N = 1, fp32, aligned: warp-per-channel kernel
         const int rc = launch_ss2d_mid_bwd(*a, (cudaStream_t)stream);
         if (rc != XFS_ERR_UNSUPPORTED) return rc;

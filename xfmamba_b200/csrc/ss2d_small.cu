@@ -287,7 +287,8 @@ ss2d_small_bwd_kernel(const xfs_ss2d_bwd_args p) {
     for (int idx = tid; idx < 4 * N * L; idx += 128) {
         const int r = idx / (N * L), rem = idx - r * N * L, n = rem / L, l = rem - n * L;
         const int pp = (r >= 2) ? L - 1 - l : l;
-        const int64_t off = (((int64_t)b * 4 + r) * N + n) * L + l;
+        const int rep = p.acc_replicas > 1 ? (int)((blockIdx.x - b * nblk) % p.acc_replicas) : 0;   // see xfscan.h
+        const int64_t off = ((((int64_t)rep * p.batch + b) * 4 + r) * N + n) * L + l;
         atomicAdd(p.dBs + off, sdB[(r * N + n) * kSmallL + pp]);
         atomicAdd(p.dCs + off, sdC[(r * N + n) * kSmallL + pp]);
     }

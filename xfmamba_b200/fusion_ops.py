@@ -145,13 +145,13 @@ def ss2d_fwd_raw(x, delta, A, Bs, Cs, Ds, delta_bias, delta_softplus=True, out_d
 def ss2d_acc_replicas(D, L):
     """Replicas of the dBs/dCs accumulators (``xfs_ss2d_bwd_args.acc_replicas``): every channel of a batch image adds into
     the same L2 lines at the same time; spreading the D channels over R copies removes that serialisation."""
-    if L <= 64:
-        return 1                      # the short-sequence kernel already sums a CTA's channels in shared memory
     env = os.environ.get("XFS_ACC_REPLICAS")
     if env:
         return max(1, min(int(env), int(D), 64))
     # measured on B200 (profiles/r01_shape_sweep.md): 4 copies recover most of the loss at 56x56 (more copies cost more in
     # zero-fills and in the final sum than they save), short rows with many channels want 8-16
+    if L <= 64:
+        return 1                      # the short-sequence kernel already sums 32 channels per CTA in shared memory (measured: no gain)
     R = 4 if L >= 2048 else (8 if D < 1024 else 16)
     return max(1, min(R, int(D)))
 
