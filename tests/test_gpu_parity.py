@@ -510,3 +510,26 @@ def test_dt_proj_bf16():
     out = dt_proj(z, w)
     assert out.dtype == torch.bfloat16
     assert rel_err(n(out), oracle.dt_proj(n(z), n(w))) < TOL16
+
+
+@pytest.mark.parametrize("shape", [(2, 6, 1, 28, 28), (2, 5, 1, 14, 14), (1, 8, 16, 7, 7)])
+def test_ss2d_bwd_accumulator_replicas_agree(xf, shape):
+    """xfs_ss2d_bwd_args.acc_replicas: dBs/dCs spread over R copies (channel d -> copy d % R) must sum to the plain result"""
+    from xfmamba_b200 import fusion_ops
+    Bsz, D, N, H, W = shape
+    rng = np.random.default_rng(11)
+    c = _rand_ss2d(rng, Bsz, D, N, H, W, False)
+    args = [t(c[k]) for k in ("x", "delta", "A", "Bs", "Cs", "Ds", "delta_bias")]
+    dy = t(rng.standard_normal((Bsz, D, H * W)).astype(np.float32))
+    y, st = fusion_ops.ss2d_fwd_raw(*args, True, torch.float32, True)
+    def run(R):
+        shp = tuple(args[3].shape) if R == 1 else (R,) + tuple(args[3].shape)
+        out = (torch.empty_like(args[0]), torch.empty_like(args[1]), torch.empty_like(args[2]),
+               torch.empty(shp, device=dev()), torch.empty(shp, device=dev()), torch.empty_like(args[5]), torch.empty_like(args[6]))
+        return [n(v) for v in fusion_ops.ss2d_bwd_raw(*args, dy, st, True, out)]
+    base = run(1)
+    for R in (3, 8):
+        got = run(R)
+        assert got[3].shape == base[3].shape
+        for a, b in zip(got, base):
+            assert rel_err(a, b) < 1e-5

@@ -13,7 +13,7 @@ from pathlib import Path
 import torch
 
 _PKG = Path(__file__).resolve().parent
-_SO = _PKG / "libxfscan.so"
+_SO = Path(os.environ["XFMAMBA_B200_LIB"]) if os.environ.get("XFMAMBA_B200_LIB") else _PKG / "libxfscan.so"
 _lib = None
 
 F32, BF16, F16 = 0, 1, 2

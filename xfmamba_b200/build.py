@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import hashlib
 import os
+import shlex
 import shutil
 import subprocess
 import sys
@@ -26,7 +27,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "--use_fast_math", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
     "-Xptxas", "-v",
-]
+] + shlex.split(os.environ.get("XFS_NVCC_EXTRA", ""))      # e.g. -DXFS_... for timing experiments (tools/)
 
 
 def _nvcc() -> str:
