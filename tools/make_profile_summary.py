@@ -71,7 +71,8 @@ for r in rows[2:]:
     lines = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, short.replace("_kernel", ""), "--top", "14"],
                            capture_output=True, text=True).stdout
     md += ["Hottest source lines (stall samples / executed instructions):", "", "```", lines.rstrip()[:6000], "```", ""]
-summ = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep], capture_output=True, text=True).stdout
+elems = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--elements=")]      # (b, k, d, l) count of the profiled launch
+summ = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep] + elems, capture_output=True, text=True).stdout
 md += ["## executed instruction mix per (b, k, d, l) element", "", "```"] + sorted(set(l[:600] for l in summ.splitlines() if l.startswith("== instr/element"))) + ["```", ""]
 if launches and os.path.exists(launches):
     md += ["## launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`, cold cache, serialised)", "",
