@@ -131,7 +131,9 @@ typedef struct {
     float* dD;               /* nullable iff D is */
     float* ddelta_bias;      /* nullable iff delta_bias is */
     int64_t batch, dim, dstate, seqlen, ngroups;
-    int32_t dtype, dout_dtype, delta_softplus, reserved;
+    int32_t dtype, dout_dtype, delta_softplus;
+    int32_t acc_replicas;    /* R > 1: dB / dC are (R, batch, ngroups, dstate, seqlen), channel d adds into copy d % R and the
+                                caller sums over R (see xfs_ss2d_bwd_args.acc_replicas); 0 or 1: plain */
 } xfs_scan_bwd_args;
 
 XFS_API int xfs_selective_scan_fwd(const xfs_scan_fwd_args* a, xfs_stream_t stream);

@@ -32,7 +32,7 @@ class ScanBwdArgs(ctypes.Structure):
     _fields_ = [(n, c_vp) for n in ("u", "delta", "A", "B", "C", "D", "delta_bias", "dout", "states", "du", "ddelta",
                                     "dA", "dB", "dC", "dD", "ddelta_bias")] + \
                [(n, c_i64) for n in ("batch", "dim", "dstate", "seqlen", "ngroups")] + \
-               [(n, c_i32) for n in ("dtype", "dout_dtype", "delta_softplus", "reserved")]
+               [(n, c_i32) for n in ("dtype", "dout_dtype", "delta_softplus", "acc_replicas")]
 
 
 class Ss2dFwdArgs(ctypes.Structure):

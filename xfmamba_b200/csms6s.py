@@ -75,6 +75,14 @@ def selective_scan_fwd_raw(u, delta, A, B, C, D, delta_bias, delta_softplus, ofl
     return out, states, (u, delta, A, B, C, D, delta_bias)
 
 
+def _acc_replicas(channels_per_group, L):
+    """copies of the dB/dC accumulators (``xfs_scan_bwd_args.acc_replicas``); short rows go through the kernel that already
+    sums 128 rows per CTA in shared memory"""
+    if L <= 64 or channels_per_group < 8:
+        return 1
+    return min(4 if L >= 2048 else 8, channels_per_group)
+
+
 def selective_scan_bwd_raw(u, delta, A, B, C, D, delta_bias, dout, states, delta_softplus):
     """mirrors ``ext.bwd(...) -> [du, ddelta, dA, dB, dC, dD, ddelta_bias]`` (selective_scan.cpp:251-260, 329-360)"""
     dev = u.device
@@ -87,18 +95,23 @@ def selective_scan_bwd_raw(u, delta, A, B, C, D, delta_bias, dout, states, delta
     du = torch.empty_like(u)
     ddelta = torch.empty_like(delta)
     dA = torch.zeros_like(A)
-    dB = torch.zeros(B.shape, dtype=torch.float32, device=dev)
-    dC = torch.zeros(C.shape, dtype=torch.float32, device=dev)
+    # dB / dC accumulators in R copies (channel d -> copy d % R): all dim/G channels of a group add into the same L2 lines
+    R = _acc_replicas(dim // G, L)
+    acc_shape = tuple(B.shape) if R == 1 else (R,) + tuple(B.shape)
+    dB = torch.zeros(acc_shape, dtype=torch.float32, device=dev)
+    dC = torch.zeros(acc_shape, dtype=torch.float32, device=dev)
     dD = None if D is None else torch.zeros_like(D)
     dbias = None if delta_bias is None else torch.zeros_like(delta_bias)
     if u.numel() > 0:
         args = _lib.ScanBwdArgs(_lib.ptr(u), _lib.ptr(delta), _lib.ptr(A), _lib.ptr(B), _lib.ptr(C), _lib.ptr(D),
                                 _lib.ptr(delta_bias), _lib.ptr(dout), _lib.ptr(states), _lib.ptr(du), _lib.ptr(ddelta),
                                 _lib.ptr(dA), _lib.ptr(dB), _lib.ptr(dC), _lib.ptr(dD), _lib.ptr(dbias),
-                                batch, dim, N, L, G, _lib.dtype_code(u), _lib.dtype_code(dout), int(bool(delta_softplus)), 0)
+                                batch, dim, N, L, G, _lib.dtype_code(u), _lib.dtype_code(dout), int(bool(delta_softplus)), R)
         with torch.cuda.device(dev):
             rc = _lib.lib().xfs_selective_scan_bwd(args, _lib.stream(dev))
         _lib.check(rc, "selective_scan_bwd")
+    if R > 1:
+        dB, dC = dB.sum(0), dC.sum(0)
     return du, ddelta, dA, dB.to(B.dtype), dC.to(C.dtype), dD, dbias
 
 

@@ -126,7 +126,7 @@ int xfs_selective_scan_bwd(const xfs_scan_bwd_args* a, xfs_stream_t stream) {
         return XFS_ERR_NULL;
     if ((a->D != nullptr) != (a->dD != nullptr) || (a->delta_bias != nullptr) != (a->ddelta_bias != nullptr)) return XFS_ERR_NULL;
     if (a->batch <= 0 || a->dim <= 0 || a->dstate <= 0 || a->seqlen <= 0 || a->ngroups <= 0) return XFS_ERR_SHAPE;
-    if (a->dim % a->ngroups != 0 || a->dstate > 256) return XFS_ERR_SHAPE;
+    if (a->dim % a->ngroups != 0 || a->dstate > 256 || a->acc_replicas < 0 || a->acc_replicas > 64) return XFS_ERR_SHAPE;
     if (bad_dtype(a->dtype) || (a->dout_dtype != XFS_F32 && a->dout_dtype != a->dtype)) return XFS_ERR_DTYPE;
     return launch_scan_bwd(*a, (cudaStream_t)stream);
 }

@@ -136,6 +136,109 @@ __global__ void __launch_bounds__(kTile* kRows) cross_merge_kernel(const T* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// whole-plane variants (scans == cross2d, H*W*4 <= 48 KB): the 32x32 tiles leave 41 % of their threads
+// idle at 56x56 and write the column-major routes in runs of at most 32 elements.  Here a CTA stages one (b, c) plane in
+// shared memory (odd pitch: the column-major pass reads it conflict free); every global access is part of a run of L.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kPlaneThreads = 256;
+constexpr size_t kPlaneSmem = 48 * 1024;
+__host__ __device__ inline unsigned plane_magic(unsigned d) { return (unsigned)((0x100000000ull + d - 1) / d); }
+
+template <typename U, bool kOneByOne>
+__global__ void __launch_bounds__(kPlaneThreads) cross_scan_plane_kernel(const U* __restrict__ x, U* __restrict__ xs, int64_t C,
+                                                                         int H, int W, unsigned mH, unsigned mW) {
+    extern __shared__ __align__(16) unsigned char plane_smem[];
+    U* tile = reinterpret_cast<U*>(plane_smem);
+    const int pitch = W | 1, L = H * W;
+    const int64_t bc = blockIdx.x, b = bc / C, c = bc % C;
+    U* __restrict__ o[4];
+    const U* __restrict__ src[4];           // one_by_one: route k reads its own image (B, 4, C, H, W)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        o[k] = xs + ((b * 4 + k) * C + c) * L;
+        src[k] = kOneByOne ? x + ((b * 4 + k) * C + c) * L : x + bc * L;
+    }
+    for (int p = threadIdx.x; p < L; p += kPlaneThreads) {
+        const U v = src[0][p];
+        if (!kOneByOne) {
+            const int h = __umulhi((unsigned)p, mW), w = p - h * W;
+            tile[h * pitch + w] = v;
+            o[2][L - 1 - p] = v;
+        } else {
+            o[2][L - 1 - p] = src[2][p];
+        }
+        o[0][p] = v;
+    }
+#pragma unroll
+    for (int k = 1; k < 4; k += 2) {        // the two column-major routes
+        if (kOneByOne) {
+            if (k == 3) __syncthreads();
+            for (int p = threadIdx.x; p < L; p += kPlaneThreads) {
+                const int h = __umulhi((unsigned)p, mW), w = p - h * W;
+                tile[h * pitch + w] = src[k][p];
+            }
+        } else if (k == 3) {
+            break;                           // same staged image: both routes were written in the k == 1 pass
+        }
+        __syncthreads();
+        for (int q = threadIdx.x; q < L; q += kPlaneThreads) {
+            const int w = __umulhi((unsigned)q, mH), h = q - w * H;
+            const U v = tile[h * pitch + w];
+            if (!kOneByOne) { o[1][q] = v; o[3][L - 1 - q] = v; }
+            else if (k == 1) o[1][q] = v;
+            else o[3][L - 1 - q] = v;
+        }
+    }
+}
+
+template <typename T, bool kOneByOne>
+__global__ void __launch_bounds__(kPlaneThreads) cross_merge_plane_kernel(const T* __restrict__ ys, T* __restrict__ y, int64_t C,
+                                                                          int H, int W, unsigned mH, unsigned mW) {
+    extern __shared__ __align__(16) unsigned char plane_smem[];
+    T* tile = reinterpret_cast<T*>(plane_smem);
+    const int pitch = W | 1, L = H * W;
+    const int64_t bc = blockIdx.x, b = bc / C, c = bc % C;
+    const T* __restrict__ s[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s[k] = ys + ((b * 4 + k) * C + c) * L;
+    if (!kOneByOne) {
+        for (int q = threadIdx.x; q < L; q += kPlaneThreads) {
+            const int w = __umulhi((unsigned)q, mH), h = q - w * H;
+            tile[h * pitch + w] = add_rn(s[1][q], s[3][L - 1 - q]);
+        }
+        __syncthreads();
+        for (int p = threadIdx.x; p < L; p += kPlaneThreads) {
+            const int h = __umulhi((unsigned)p, mW), w = p - h * W;
+            y[bc * L + p] = add_rn(add_rn(s[0][p], s[2][L - 1 - p]), tile[h * pitch + w]);
+        }
+    } else {                                 // (B, 4, C, L) out: every route back in spatial order, no sum
+        T* __restrict__ o = y + (b * 4 * C + c) * L;
+        const int64_t ks = C * L;
+        for (int p = threadIdx.x; p < L; p += kPlaneThreads) { o[p] = s[0][p]; o[2 * ks + p] = s[2][L - 1 - p]; }
+#pragma unroll
+        for (int k = 1; k < 4; k += 2) {
+            if (k == 3) __syncthreads();
+            for (int q = threadIdx.x; q < L; q += kPlaneThreads) {
+                const int w = __umulhi((unsigned)q, mH), h = q - w * H;
+                tile[h * pitch + w] = (k == 1) ? s[1][q] : s[3][L - 1 - q];
+            }
+            __syncthreads();
+            for (int p = threadIdx.x; p < L; p += kPlaneThreads) {
+                const int h = __umulhi((unsigned)p, mW), w = p - h * W;
+                o[k * ks + p] = tile[h * pitch + w];
+            }
+        }
+    }
+}
+
+static bool plane_ok(int64_t H, int64_t W, int scans, int one_by_one, size_t esize) {
+    // the index magic needs n * d < 2^32 for n < H*W, d = H or W; the plane (odd pitch) must fit the default 48 KB
+    (void)one_by_one;
+    return scans == XFS_SCANS_CROSS2D && H >= 2 && W >= 2 && H * W <= 16384 &&
+           (size_t)H * (size_t)(W | 1) * esize <= kPlaneSmem;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // swap scan / merge / stack: row copies, 16 bytes per thread when rows allow
 // mode 0: scan  (x, x2) -> out (B,2,C,L)  even channels exchanged
 // mode 1: merge ys -> (y, y2)             plain split
@@ -167,6 +270,16 @@ __global__ void __launch_bounds__(256) swap_kernel(const V* __restrict__ a, cons
 // ---------------------------------------------------------------------------------------------------------
 int launch_cross_scan(const void* x, void* xs, int64_t B, int64_t C, int64_t H, int64_t W, int dtype, int scans,
                       int one_by_one, cudaStream_t st) {
+    const size_t esize = dtype == XFS_F32 ? 4 : 2;
+    if (plane_ok(H, W, scans, one_by_one, esize)) {
+        const size_t smem = (size_t)H * (size_t)(W | 1) * esize;
+        const unsigned mH = plane_magic((unsigned)H), mW = plane_magic((unsigned)W);
+#define XFS_PLANE_SCAN(U, OBO) cross_scan_plane_kernel<U, OBO><<<(unsigned)(B * C), kPlaneThreads, smem, st>>>((const U*)x, (U*)xs, C, (int)H, (int)W, mH, mW)
+        if (dtype == XFS_F32) { if (one_by_one) XFS_PLANE_SCAN(uint32_t, true); else XFS_PLANE_SCAN(uint32_t, false); }
+        else { if (one_by_one) XFS_PLANE_SCAN(uint16_t, true); else XFS_PLANE_SCAN(uint16_t, false); }
+#undef XFS_PLANE_SCAN
+        return check_launch();
+    }
     dim3 grid((unsigned)(B * C), (unsigned)((H + kTile - 1) / kTile), (unsigned)((W + kTile - 1) / kTile));
     dim3 block(kTile, kRows);
     if (dtype == XFS_F32)
@@ -178,6 +291,17 @@ int launch_cross_scan(const void* x, void* xs, int64_t B, int64_t C, int64_t H, 
 
 int launch_cross_merge(const void* ys, void* y, int64_t B, int64_t C, int64_t H, int64_t W, int dtype, int scans,
                        int one_by_one, cudaStream_t st) {
+    const size_t esize = dtype == XFS_F32 ? 4 : 2;
+    if (plane_ok(H, W, scans, one_by_one, esize)) {
+        const size_t smem = (size_t)H * (size_t)(W | 1) * esize;
+        const unsigned mH = plane_magic((unsigned)H), mW = plane_magic((unsigned)W);
+#define XFS_PLANE_MERGE(T, OBO) cross_merge_plane_kernel<T, OBO><<<(unsigned)(B * C), kPlaneThreads, smem, st>>>((const T*)ys, (T*)y, C, (int)H, (int)W, mH, mW)
+        if (dtype == XFS_F32) { if (one_by_one) XFS_PLANE_MERGE(float, true); else XFS_PLANE_MERGE(float, false); }
+        else if (dtype == XFS_BF16) { if (one_by_one) XFS_PLANE_MERGE(__nv_bfloat16, true); else XFS_PLANE_MERGE(__nv_bfloat16, false); }
+        else { if (one_by_one) XFS_PLANE_MERGE(__half, true); else XFS_PLANE_MERGE(__half, false); }
+#undef XFS_PLANE_MERGE
+        return check_launch();
+    }
     dim3 grid((unsigned)(B * C), (unsigned)((H + kTile - 1) / kTile), (unsigned)((W + kTile - 1) / kTile));
     dim3 block(kTile, kRows);
     if (dtype == XFS_F32)

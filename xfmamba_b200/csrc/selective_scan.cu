@@ -112,8 +112,12 @@ sscan_bwd_kernel(const xfs_scan_bwd_args p) {
     const TDO* __restrict__ dy_row = reinterpret_cast<const TDO*>(p.dout) + seq * L;
     const T* __restrict__ Bg = reinterpret_cast<const T*>(p.B) + (b * p.ngroups + g) * N * L;
     const T* __restrict__ Cg = reinterpret_cast<const T*>(p.C) + (b * p.ngroups + g) * N * L;
-    float* __restrict__ dBg = p.dB + (b * p.ngroups + g) * N * L;
-    float* __restrict__ dCg = p.dC + (b * p.ngroups + g) * N * L;
+    // every channel of a group adds into the same dB / dC rows: spread them over acc_replicas copies (xfscan.h) and use
+    // 16-byte vector reductions where rows allow -- scalar atomics on shared lines were 8x the operations and serialised in L2
+    const int64_t rep = p.acc_replicas > 1 ? d % p.acc_replicas : 0;
+    float* __restrict__ dBg = p.dB + ((rep * p.batch + b) * p.ngroups + g) * N * L;
+    float* __restrict__ dCg = p.dC + ((rep * p.batch + b) * p.ngroups + g) * N * L;
+    const bool vacc = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.dB) | reinterpret_cast<uintptr_t>(p.dC)) & 15) == 0;
     T* __restrict__ du_row = reinterpret_cast<T*>(p.du) + seq * L;
     T* __restrict__ ddt_row = reinterpret_cast<T*>(p.ddelta) + seq * L;
     const bool vin = row_vec_ok(reinterpret_cast<const T*>(p.u), L) && row_vec_ok(reinterpret_cast<const T*>(p.delta), L) &&
@@ -178,7 +182,7 @@ sscan_bwd_kernel(const xfs_scan_bwd_args p) {
             }
             float q_out;
             const float q_in = warp_prefix<true>(Pr, Sr, s_q[wib][n], lane, q_out);
-            float dA_part = 0.0f;
+            float dA_part = 0.0f, dBv[8], dCv[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float h = fmaf(P[i], h_in, S[i]);
@@ -188,10 +192,25 @@ sscan_bwd_kernel(const xfs_scan_bwd_args p) {
                 du[i] = fmaf(gi * dt[i], Bv[i], du[i]);
                 ddt[i] = fmaf(gi, fmaf(Bv[i], u[i], An * hp), ddt[i]);
                 dA_part = fmaf(gi * dt[i], hp, dA_part);
-                if (l0 + i < L) {
-                    atomicAdd(dBg + n * L + l0 + i, gi * dt[i] * u[i]);
-                    atomicAdd(dCg + n * L + l0 + i, dy[i] * h);
+                dBv[i] = gi * dt[i] * u[i];
+                dCv[i] = dy[i] * h;
+            }
+            if (vacc) {         // L % 4 == 0: a 16-byte granule is entirely inside or outside the row
+                if (l0 + 4 <= L) {
+                    red_add_v4(dBg + n * L + l0, dBv[0], dBv[1], dBv[2], dBv[3]);
+                    red_add_v4(dCg + n * L + l0, dCv[0], dCv[1], dCv[2], dCv[3]);
                 }
+                if (l0 + 8 <= L) {
+                    red_add_v4(dBg + n * L + l0 + 4, dBv[4], dBv[5], dBv[6], dBv[7]);
+                    red_add_v4(dCg + n * L + l0 + 4, dCv[4], dCv[5], dCv[6], dCv[7]);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (l0 + i < L) {
+                        atomicAdd(dBg + n * L + l0 + i, dBv[i]);
+                        atomicAdd(dCg + n * L + l0 + i, dCv[i]);
+                    }
             }
             dA_part = warp_sum(dA_part);
             __syncwarp();
