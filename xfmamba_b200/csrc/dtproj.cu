@@ -23,29 +23,34 @@ constexpr int kDtCh = 8;             // channels per thread
 struct DtGeom {
     int D, R, L, K;
     int PG, NCG, items, zpitch;     // zpitch: floats per z row in shared memory
+    int PGL, NB, B;                 // short rows: a CTA covers NB images, PGL position groups each (PG = NB * PGL)
     int64_t z_sb, z_sk;             // element strides of z between batches and routes (rows are contiguous: stride L)
     bool vec;                        // 16-byte loads/stores allowed (L % 4 == 0 and aligned bases/strides)
 };
 
 // ---- forward -----------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool kMulti>      // kMulti: short rows, several images per CTA (see dt_geom)
 __global__ void __launch_bounds__(kDtThreads)
 dtproj_fwd_kernel(const T* __restrict__ z, const float* __restrict__ W, T* __restrict__ out, const DtGeom g) {
     extern __shared__ __align__(16) float smem[];
     float* sz = smem;                         // [R][zpitch]
     float* sw = smem + g.R * g.zpitch;        // [R][kDtCh * NCG][2]: every weight stored twice, a ready operand pair for FFMA2
     const int tid = threadIdx.x;
-    const int bk = blockIdx.z, b = bk / g.K, k = bk - b * g.K;
-    const int l0 = blockIdx.x * (4 * g.PG), d0 = blockIdx.y * (kDtCh * g.NCG);
-    const T* __restrict__ zb = z + (int64_t)b * g.z_sb + (int64_t)k * g.z_sk;
+    const int bgk = blockIdx.z, bg = bgk / g.K, k = bgk - bg * g.K;
+    const int b0 = bg * g.NB;                                   // first image of this CTA
+    const int l0 = kMulti ? 0 : blockIdx.x * (4 * g.PG), d0 = blockIdx.y * (kDtCh * g.NCG);
+    const T* __restrict__ zk = z + (int64_t)k * g.z_sk;
+    const T* __restrict__ zb0 = zk + (int64_t)b0 * g.z_sb;       // single-image path: everything below is relative to this
     const int wcols = kDtCh * g.NCG;
 
     // z tile: R rows of up to 4*PG positions
     if (g.vec) {
         for (int i = tid; i < g.R * g.PG; i += kDtThreads) {
-            const int r = i / g.PG, pg = i - r * g.PG, l = l0 + 4 * pg;
+            const int r = i / g.PG, pg = i - r * g.PG;
+            const int bl = kMulti ? pg / g.PGL : 0, l = l0 + 4 * (pg - bl * g.PGL);
+            const T* __restrict__ zb = kMulti ? zk + (int64_t)(b0 + bl) * g.z_sb : zb0;
             float v[4] = {0.f, 0.f, 0.f, 0.f};
-            if (l < g.L) {
+            if (l < g.L && (!kMulti || b0 + bl < g.B)) {
                 if constexpr (sizeof(T) == 4) {
                     const float4 a = __ldg(reinterpret_cast<const float4*>(zb + (int64_t)r * g.L + l));
                     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
@@ -60,8 +65,10 @@ dtproj_fwd_kernel(const T* __restrict__ z, const float* __restrict__ W, T* __res
         }
     } else {
         for (int i = tid; i < g.R * 4 * g.PG; i += kDtThreads) {
-            const int r = i / (4 * g.PG), c = i - r * (4 * g.PG), l = l0 + c;
-            sz[r * g.zpitch + c] = (l < g.L) ? Elem<T>::to_f(zb[(int64_t)r * g.L + l]) : 0.0f;
+            const int r = i / (4 * g.PG), c = i - r * (4 * g.PG);
+            const int bl = kMulti ? c / (4 * g.PGL) : 0, l = l0 + c - bl * (4 * g.PGL);
+            const T* __restrict__ zb = kMulti ? zk + (int64_t)(b0 + bl) * g.z_sb : zb0;
+            sz[r * g.zpitch + c] = (l < g.L && (!kMulti || b0 + bl < g.B)) ? Elem<T>::to_f(zb[(int64_t)r * g.L + l]) : 0.0f;
         }
     }
     // W tile transposed to [r][channel], duplicated
@@ -91,11 +98,12 @@ dtproj_fwd_kernel(const T* __restrict__ z, const float* __restrict__ W, T* __res
                 acc[2 * h + 1][0] = fma2(z01, wb, acc[2 * h + 1][0]); acc[2 * h + 1][1] = fma2(z23, wb, acc[2 * h + 1][1]);
             }
         }
-        const int l = l0 + 4 * pg;
+        const int bl = kMulti ? pg / g.PGL : 0, l = l0 + 4 * (pg - bl * g.PGL);
+        const int bk = (b0 + bl) * g.K + k;
 #pragma unroll
         for (int c = 0; c < kDtCh; ++c) {
             const int d = d0 + kDtCh * cg + c;
-            if (d >= g.D || l >= g.L) continue;
+            if (d >= g.D || l >= g.L || (kMulti && b0 + bl >= g.B)) continue;
             T* __restrict__ o = out + ((int64_t)bk * g.D + d) * g.L + l;
             const float v[4] = {acc[c][0].x, acc[c][0].y, acc[c][1].x, acc[c][1].y};
             if (g.vec) {
@@ -116,11 +124,20 @@ dtproj_fwd_kernel(const T* __restrict__ z, const float* __restrict__ W, T* __res
     }
 }
 
-static DtGeom dt_geom(int64_t D, int64_t R, int64_t L, int64_t K, int64_t z_sb, int64_t z_sk, bool aligned) {
+static DtGeom dt_geom(int64_t B, int64_t D, int64_t R, int64_t L, int64_t K, int64_t z_sb, int64_t z_sk, bool aligned) {
     DtGeom g;
-    g.D = (int)D; g.R = (int)R; g.L = (int)L; g.K = (int)K;
+    g.D = (int)D; g.R = (int)R; g.L = (int)L; g.K = (int)K; g.B = (int)B;
     const int pgs = (int)((L + 3) / 4);
-    g.PG = pgs < kDtMaxPG ? pgs : kDtMaxPG;
+    if (pgs * 2 <= kDtMaxPG) {           // short rows (L <= 128): several images share a CTA and its weight tile
+        g.PGL = pgs;
+        g.NB = kDtMaxPG / pgs;
+        if (g.NB > B) g.NB = (int)B;
+        g.PG = g.NB * g.PGL;
+    } else {
+        g.PG = pgs < kDtMaxPG ? pgs : kDtMaxPG;
+        g.PGL = g.PG;
+        g.NB = 1;
+    }
     // channel groups (of 8) per CTA: as many as 8 (fewer re-reads of the z tile), chosen so that NCG * PG items fill whole
     // rounds of the 256 threads (L = 196 -> PG = 49 -> NCG = 5: 245 items in one round, 96 % of the lanes busy)
     const int cgs = (int)((D + kDtCh - 1) / kDtCh);
@@ -145,20 +162,21 @@ int launch_dtproj_fwd(const void* z, const float* W, void* out, int64_t B, int64
     if (R > kDtMaxRank) return XFS_ERR_UNSUPPORTED;
     const int esz = dtype == XFS_F32 ? 4 : 2;
     const bool aligned = ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(out)) % (4 * esz)) == 0;
-    const DtGeom g = dt_geom(D, R, L, K, z_sb, z_sk, aligned);
-    const dim3 grid((unsigned)((L + 4 * g.PG - 1) / (4 * g.PG)), (unsigned)((D + kDtCh * g.NCG - 1) / (kDtCh * g.NCG)), (unsigned)(B * K));
+    const DtGeom g = dt_geom(B, D, R, L, K, z_sb, z_sk, aligned);
+    const unsigned ltiles = g.NB > 1 ? 1u : (unsigned)((L + 4 * g.PG - 1) / (4 * g.PG));
+    const dim3 grid(ltiles, (unsigned)((D + kDtCh * g.NCG - 1) / (kDtCh * g.NCG)), (unsigned)(((B + g.NB - 1) / g.NB) * K));
     if (grid.y > 65535 || grid.z > 65535) return XFS_ERR_SHAPE;
     const size_t smem = sizeof(float) * ((size_t)g.R * g.zpitch + (size_t)g.R * 2 * kDtCh * g.NCG);
-    if (dtype == XFS_F32) {
-        cudaFuncSetAttribute(dtproj_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        dtproj_fwd_kernel<float><<<grid, kDtThreads, smem, st>>>((const float*)z, W, (float*)out, g);
-    } else if (dtype == XFS_BF16) {
-        cudaFuncSetAttribute(dtproj_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        dtproj_fwd_kernel<__nv_bfloat16><<<grid, kDtThreads, smem, st>>>((const __nv_bfloat16*)z, W, (__nv_bfloat16*)out, g);
-    } else {
-        cudaFuncSetAttribute(dtproj_fwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        dtproj_fwd_kernel<__half><<<grid, kDtThreads, smem, st>>>((const __half*)z, W, (__half*)out, g);
-    }
+#define XFS_DT_LAUNCH(T, M)                                                                                             \
+    do {                                                                                                                \
+        cudaFuncSetAttribute(dtproj_fwd_kernel<T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+        dtproj_fwd_kernel<T, M><<<grid, kDtThreads, smem, st>>>((const T*)z, W, (T*)out, g);                             \
+    } while (0)
+    const bool multi = g.NB > 1;
+    if (dtype == XFS_F32) { if (multi) XFS_DT_LAUNCH(float, true); else XFS_DT_LAUNCH(float, false); }
+    else if (dtype == XFS_BF16) { if (multi) XFS_DT_LAUNCH(__nv_bfloat16, true); else XFS_DT_LAUNCH(__nv_bfloat16, false); }
+    else { if (multi) XFS_DT_LAUNCH(__half, true); else XFS_DT_LAUNCH(__half, false); }
+#undef XFS_DT_LAUNCH
     return check_launch();
 }
 
