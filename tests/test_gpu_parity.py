@@ -315,9 +315,10 @@ def test_ss2d_fused_oracle_fp32(xf, shape, model_like):
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("oflex", [True, False])
-def test_ss2d_fused_16bit(xf, dtype, oflex):
+@pytest.mark.parametrize("hw", [(16, 24), (14, 14), (9, 12), (7, 7)])      # general / one-chunk (L % 8 != 0 and == 0) / short
+def test_ss2d_fused_16bit(xf, dtype, oflex, hw):
     rng = np.random.default_rng(11)
-    c = _rand_ss2d(rng, 2, 4, 1, 16, 24)
+    c = _rand_ss2d(rng, 2, 5, 1, hw[0], hw[1])
     for k in ("x", "delta", "Bs", "Cs"):
         c[k] = t(c[k]).to(dtype).float().cpu().numpy()
     y, leaves = _run_ss2d(xf, c, dtype, oflex)

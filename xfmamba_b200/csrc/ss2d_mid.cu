@@ -1,4 +1,4 @@
-// ss2d_mid.cu -- fused SS2D forward / backward for sequences that fit ONE chunk: 64 < L = H*W <= 256, N = 1, fp32.
+// ss2d_mid.cu -- fused SS2D forward / backward for sequences that fit ONE chunk: 64 < L = H*W <= 256, L % 4 == 0, N = 1.
 //
 // XFMamba's third backbone stage (14x14 tokens, 8 or 15 of the 14 / 21 blocks) lives here, and 16x16 at 512^2 input.  In
 // the general kernels a CTA is four route-warps around four shared image buffers; with a single chunk per route all of
@@ -62,6 +62,31 @@ __device__ __forceinline__ void mid_transpose(float* tile, const float (&src)[8]
     for (int i = 0; i < 8; ++i) dst[i] = tile[gather[i]];
 }
 
+// two granules of 4 elements (16 bytes fp32, 8 bytes bf16 / f16) at element offsets g0, g1 of a row whose start is granule aligned
+template <typename T>
+__device__ __forceinline__ void mid_load8(const T* __restrict__ row, int g0, int g1, float (&v)[8]) {
+    if constexpr (sizeof(T) == 4) {
+        load8_at<T>(row, g0, g1, v);
+    } else {
+        const uint2 a = __ldg(reinterpret_cast<const uint2*>(row + g0)), b = __ldg(reinterpret_cast<const uint2*>(row + g1));
+        const T* ea = reinterpret_cast<const T*>(&a);
+        const T* eb = reinterpret_cast<const T*>(&b);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[i] = Elem<T>::to_f(ea[i]); v[4 + i] = Elem<T>::to_f(eb[i]); }
+    }
+}
+template <typename T>
+__device__ __forceinline__ void mid_store4(T* __restrict__ ptr, float a, float b, float c, float d) {
+    if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(ptr) = make_float4(a, b, c, d);
+    } else {
+        uint2 o;
+        T* e = reinterpret_cast<T*>(&o);
+        e[0] = Elem<T>::from_f(a); e[1] = Elem<T>::from_f(b); e[2] = Elem<T>::from_f(c); e[3] = Elem<T>::from_f(d);
+        *reinterpret_cast<uint2*>(ptr) = o;
+    }
+}
+
 // delta / B / C of one route in ADDRESS order plus its three parameters, exactly as loaded.  The loads of route k+1 are
 // issued (in program order) BEFORE route k is computed: each warp then pays one exposed memory round trip, not four.
 struct MidLoads {
@@ -69,14 +94,14 @@ struct MidLoads {
     float bias, Dd, A;
 };
 
-template <bool kRev>
-__device__ __forceinline__ void mid_issue(MidLoads& r, const float* __restrict__ dt_row, const float* __restrict__ Brow,
-                                          const float* __restrict__ Crow, const float* __restrict__ A, const float* __restrict__ Ds,
+template <bool kRev, typename T>
+__device__ __forceinline__ void mid_issue(MidLoads& r, const T* __restrict__ dt_row, const T* __restrict__ Brow,
+                                          const T* __restrict__ Crow, const float* __restrict__ A, const float* __restrict__ Ds,
                                           const float* __restrict__ dbias, int kd, const MidLane& m) {
     const int g0 = kRev ? m.g0r : m.g0f, g1 = kRev ? m.g1r : m.g1f;
-    load8_at<float>(dt_row, g0, g1, r.dt);
-    load8_at<float>(Brow, g0, g1, r.B);
-    load8_at<float>(Crow, g0, g1, r.C);
+    mid_load8<T>(dt_row, g0, g1, r.dt);
+    mid_load8<T>(Brow, g0, g1, r.B);
+    mid_load8<T>(Crow, g0, g1, r.C);
     r.bias = dbias ? __ldg(dbias + kd) : 0.0f;
     r.Dd = Ds ? __ldg(Ds + kd) : 0.0f;
     r.A = __ldg(A + kd);
@@ -134,6 +159,7 @@ __device__ __forceinline__ void mid_route_fwd(const xfs_ss2d_fwd_args& p, const 
     }
 }
 
+template <typename T, typename TO>
 __global__ void __launch_bounds__(kMidWarps * 32, 4)
 ss2d_mid_fwd_kernel(const xfs_ss2d_fwd_args p) {
     __shared__ __align__(16) float tiles[kMidWarps][kMidTile];
@@ -145,19 +171,19 @@ ss2d_mid_fwd_kernel(const xfs_ss2d_fwd_args p) {
     float* tile = tiles[wp];
     const MidLane m = mid_lane(lane, L);
 
-    const float* __restrict__ xrow = reinterpret_cast<const float*>(p.x) + chan * L;
-    const float* __restrict__ delta = reinterpret_cast<const float*>(p.delta) + (int64_t)b * 4 * D * L;
-    const float* __restrict__ Bs = reinterpret_cast<const float*>(p.Bs) + (int64_t)b * 4 * L;
-    const float* __restrict__ Cs = reinterpret_cast<const float*>(p.Cs) + (int64_t)b * 4 * L;
+    const T* __restrict__ xrow = reinterpret_cast<const T*>(p.x) + chan * L;
+    const T* __restrict__ delta = reinterpret_cast<const T*>(p.delta) + (int64_t)b * 4 * D * L;
+    const T* __restrict__ Bs = reinterpret_cast<const T*>(p.Bs) + (int64_t)b * 4 * L;
+    const T* __restrict__ Cs = reinterpret_cast<const T*>(p.Cs) + (int64_t)b * 4 * L;
     float* st = p.states ? p.states + (int64_t)b * 4 * D : nullptr;       // (B, 4D, 1, 1)
 #define XFS_MID_ISSUE(R, K, REV)                                                                                                      \
-    mid_issue<REV>(R, delta + (int64_t)((K) * D + d) * L, Bs + (K) * L, Cs + (K) * L, p.A, p.Ds, p.delta_bias, (K) * D + d, m)
+    mid_issue<REV, T>(R, delta + (int64_t)((K) * D + d) * L, Bs + (K) * L, Cs + (K) * L, p.A, p.Ds, p.delta_bias, (K) * D + d, m)
     // every load the first two routes need is issued before the first loaded value is touched (in-order issue: the warp
     // stalls at the first use, and whatever has not been issued by then waits behind it)
     MidLoads ra, rb;
     float u[8], uT[8];
     XFS_MID_ISSUE(ra, 0, false);
-    load8_at<float>(xrow, m.g0f, m.g1f, u);
+    mid_load8<T>(xrow, m.g0f, m.g1f, u);
     XFS_MID_ISSUE(rb, 2, true);
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -182,16 +208,16 @@ ss2d_mid_fwd_kernel(const xfs_ss2d_fwd_args p) {
     mid_transposed_index(m.p0, H, W, L, sc);
     float back[8];
     mid_transpose(tile, yT, back, sc, m.p0);
-    float* __restrict__ yrow = reinterpret_cast<float*>(p.y) + chan * L;
-    if (m.ok0) *reinterpret_cast<float4*>(yrow + m.p0) = make_float4(yN[0] + back[0], yN[1] + back[1], yN[2] + back[2], yN[3] + back[3]);
-    if (m.ok1) *reinterpret_cast<float4*>(yrow + m.p0 + 4) = make_float4(yN[4] + back[4], yN[5] + back[5], yN[6] + back[6], yN[7] + back[7]);
+    TO* __restrict__ yrow = reinterpret_cast<TO*>(p.y) + chan * L;
+    if (m.ok0) mid_store4<TO>(yrow + m.p0, yN[0] + back[0], yN[1] + back[1], yN[2] + back[2], yN[3] + back[3]);
+    if (m.ok1) mid_store4<TO>(yrow + m.p0 + 4, yN[4] + back[4], yN[5] + back[5], yN[6] + back[6], yN[7] + back[7]);
 }
 
 
 // ---- one route of the backward ------------------------------------------------------------------------------------------
 // u, dy: this route's position order (row-major for routes 0/2, column-major for 1/3); du accumulates in the same order.
-template <bool kRev>
-__device__ __forceinline__ void mid_route_bwd(const xfs_ss2d_bwd_args& p, const MidLoads& r, float* __restrict__ ddt_row,
+template <bool kRev, typename T>
+__device__ __forceinline__ void mid_route_bwd(const xfs_ss2d_bwd_args& p, const MidLoads& r, T* __restrict__ ddt_row,
                                               float* __restrict__ dBrow, float* __restrict__ dCrow, const MidLane& m, int L, int lane,
                                               const float (&u)[8], const float (&dy)[8], float (&du)[8], float (&pg)[3]) {
     const int g0 = kRev ? m.g0r : m.g0f, g1 = kRev ? m.g1r : m.g1f;
@@ -267,8 +293,8 @@ __device__ __forceinline__ void mid_route_bwd(const xfs_ss2d_bwd_args& p, const 
     float v[8], va[8];
     unpack8(ddt2, v); to_pos<kRev>(v, va);
     const bool okA = kRev ? m.ok1 : m.ok0, okB = kRev ? m.ok0 : m.ok1;      // validity of the low / high ADDRESS granule
-    if (okA) *reinterpret_cast<float4*>(ddt_row + g0) = make_float4(va[0], va[1], va[2], va[3]);
-    if (okB) *reinterpret_cast<float4*>(ddt_row + g1) = make_float4(va[4], va[5], va[6], va[7]);
+    if (okA) mid_store4<T>(ddt_row + g0, va[0], va[1], va[2], va[3]);
+    if (okB) mid_store4<T>(ddt_row + g1, va[4], va[5], va[6], va[7]);
     unpack8(dB2, v); to_pos<kRev>(v, va);
     if (okA) red_add_v4_relaxed(dBrow + g0, va[0], va[1], va[2], va[3]);
     if (okB) red_add_v4_relaxed(dBrow + g1, va[4], va[5], va[6], va[7]);
@@ -279,6 +305,7 @@ __device__ __forceinline__ void mid_route_bwd(const xfs_ss2d_bwd_args& p, const 
     pg[0] = dA2.x + dA2.y; pg[1] = dD2.x + dD2.y; pg[2] = dbias2.x + dbias2.y;
 }
 
+template <typename T, typename TDO>
 __global__ void __launch_bounds__(kMidWarps * 32, 3)
 ss2d_mid_bwd_kernel(const xfs_ss2d_bwd_args p) {
     __shared__ __align__(16) float tiles[kMidWarps][kMidTile];
@@ -290,22 +317,22 @@ ss2d_mid_bwd_kernel(const xfs_ss2d_bwd_args p) {
     float* tile = tiles[wp];
     const MidLane m = mid_lane(lane, L);
 
-    const float* __restrict__ delta = reinterpret_cast<const float*>(p.delta) + (int64_t)b * 4 * D * L;
-    float* __restrict__ ddelta = reinterpret_cast<float*>(p.ddelta) + (int64_t)b * 4 * D * L;
-    const float* __restrict__ Bs = reinterpret_cast<const float*>(p.Bs) + (int64_t)b * 4 * L;
-    const float* __restrict__ Cs = reinterpret_cast<const float*>(p.Cs) + (int64_t)b * 4 * L;
+    const T* __restrict__ delta = reinterpret_cast<const T*>(p.delta) + (int64_t)b * 4 * D * L;
+    T* __restrict__ ddelta = reinterpret_cast<T*>(p.ddelta) + (int64_t)b * 4 * D * L;
+    const T* __restrict__ Bs = reinterpret_cast<const T*>(p.Bs) + (int64_t)b * 4 * L;
+    const T* __restrict__ Cs = reinterpret_cast<const T*>(p.Cs) + (int64_t)b * 4 * L;
     const int rep = p.acc_replicas > 1 ? d % p.acc_replicas : 0;        // accumulator replica of this channel (see xfscan.h)
     float* __restrict__ dBs = p.dBs + ((int64_t)rep * p.batch + b) * 4 * L;
     float* __restrict__ dCs = p.dCs + ((int64_t)rep * p.batch + b) * 4 * L;
 #define XFS_MID_ISSUE(R, K, REV)                                                                                                      \
-    mid_issue<REV>(R, delta + (int64_t)((K) * D + d) * L, Bs + (K) * L, Cs + (K) * L, p.A, p.Ds, p.delta_bias, (K) * D + d, m)
+    mid_issue<REV, T>(R, delta + (int64_t)((K) * D + d) * L, Bs + (K) * L, Cs + (K) * L, p.A, p.Ds, p.delta_bias, (K) * D + d, m)
 #define XFS_MID_ROUTE(R, K, REV, U, DY, DU)                                                                                           \
-    mid_route_bwd<REV>(p, R, ddelta + (int64_t)((K) * D + d) * L, dBs + (K) * L, dCs + (K) * L, m, L, lane, U, DY, DU, pg[K])
+    mid_route_bwd<REV, T>(p, R, ddelta + (int64_t)((K) * D + d) * L, dBs + (K) * L, dCs + (K) * L, m, L, lane, U, DY, DU, pg[K])
     MidLoads ra, rb;
     float u[8], dy[8], duN[8], pg[4][3];
     XFS_MID_ISSUE(ra, 0, false);         // everything routes 0 and 2 need, issued before the first use (see the forward)
-    load8_at<float>(reinterpret_cast<const float*>(p.x) + chan * L, m.g0f, m.g1f, u);
-    load8_at<float>(reinterpret_cast<const float*>(p.dy) + chan * L, m.g0f, m.g1f, dy);
+    mid_load8<T>(reinterpret_cast<const T*>(p.x) + chan * L, m.g0f, m.g1f, u);
+    mid_load8<TDO>(reinterpret_cast<const TDO*>(p.dy) + chan * L, m.g0f, m.g1f, dy);
     XFS_MID_ISSUE(rb, 2, true);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -349,9 +376,9 @@ ss2d_mid_bwd_kernel(const xfs_ss2d_bwd_args p) {
     mid_transposed_index(m.p0, H, W, L, sc);
     float back[8];
     mid_transpose(tile, duT, back, sc, m.p0);
-    float* __restrict__ dxrow = reinterpret_cast<float*>(p.dx) + chan * L;
-    if (m.ok0) *reinterpret_cast<float4*>(dxrow + m.p0) = make_float4(duN[0] + back[0], duN[1] + back[1], duN[2] + back[2], duN[3] + back[3]);
-    if (m.ok1) *reinterpret_cast<float4*>(dxrow + m.p0 + 4) = make_float4(duN[4] + back[4], duN[5] + back[5], duN[6] + back[6], duN[7] + back[7]);
+    T* __restrict__ dxrow = reinterpret_cast<T*>(p.dx) + chan * L;
+    if (m.ok0) mid_store4<T>(dxrow + m.p0, duN[0] + back[0], duN[1] + back[1], duN[2] + back[2], duN[3] + back[3]);
+    if (m.ok1) mid_store4<T>(dxrow + m.p0 + 4, duN[4] + back[4], duN[5] + back[5], duN[6] + back[6], duN[7] + back[7]);
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------
@@ -360,27 +387,41 @@ int ss2d_mid_supported(int64_t N, int64_t H, int64_t W) {
     return N == 1 && L > kSmallL && L <= kChunk && (L % 4 == 0);
 }
 
-static bool mid_ptrs_ok(std::initializer_list<const void*> ps) {
+// granule alignment: 16 bytes for 4-byte elements, 8 bytes for 2-byte ones (dBs/dCs are always fp32)
+static bool mid_ptrs_ok(std::initializer_list<const void*> ps, size_t align) {
     for (const void* q : ps)
-        if (q && !aligned16(q)) return false;
+        if (q && (reinterpret_cast<uintptr_t>(q) % align) != 0) return false;
     return true;
 }
 
-// returns XFS_ERR_UNSUPPORTED when the dtype / alignment preconditions do not hold (the caller then takes the general kernels)
+// returns XFS_ERR_UNSUPPORTED when the alignment preconditions do not hold (the caller then takes the general kernels)
 int launch_ss2d_mid_fwd(const xfs_ss2d_fwd_args& a, cudaStream_t st) {
-    if (a.dtype != XFS_F32 || a.out_dtype != XFS_F32 || !mid_ptrs_ok({a.x, a.delta, a.Bs, a.Cs, a.y})) return XFS_ERR_UNSUPPORTED;
+    const size_t al = a.dtype == XFS_F32 ? 16 : 8;
+    if (!mid_ptrs_ok({a.x, a.delta, a.Bs, a.Cs}, al) || !mid_ptrs_ok({a.y}, a.out_dtype == XFS_F32 ? 16 : 8)) return XFS_ERR_UNSUPPORTED;
     const int64_t chans = a.batch * a.D;
     const unsigned grid = (unsigned)((chans + kMidWarps - 1) / kMidWarps);
-    ss2d_mid_fwd_kernel<<<grid, kMidWarps * 32, 0, st>>>(a);
+    const bool o32 = a.out_dtype == XFS_F32;
+#define XFS_MID_FWD(T, TO) ss2d_mid_fwd_kernel<T, TO><<<grid, kMidWarps * 32, 0, st>>>(a)
+    if (a.dtype == XFS_F32) XFS_MID_FWD(float, float);
+    else if (a.dtype == XFS_BF16) { if (o32) XFS_MID_FWD(__nv_bfloat16, float); else XFS_MID_FWD(__nv_bfloat16, __nv_bfloat16); }
+    else { if (o32) XFS_MID_FWD(__half, float); else XFS_MID_FWD(__half, __half); }
+#undef XFS_MID_FWD
     return check_launch();
 }
 
 int launch_ss2d_mid_bwd(const xfs_ss2d_bwd_args& a, cudaStream_t st) {
-    if (a.dtype != XFS_F32 || a.dout_dtype != XFS_F32 || !mid_ptrs_ok({a.x, a.delta, a.Bs, a.Cs, a.dy, a.dx, a.ddelta, a.dBs, a.dCs}))
+    const size_t al = a.dtype == XFS_F32 ? 16 : 8;
+    if (!mid_ptrs_ok({a.x, a.delta, a.Bs, a.Cs, a.dx, a.ddelta}, al) || !mid_ptrs_ok({a.dy}, a.dout_dtype == XFS_F32 ? 16 : 8) ||
+        !mid_ptrs_ok({a.dBs, a.dCs}, 16))
         return XFS_ERR_UNSUPPORTED;
     const int64_t chans = a.batch * a.D;
     const unsigned grid = (unsigned)((chans + kMidWarps - 1) / kMidWarps);
-    ss2d_mid_bwd_kernel<<<grid, kMidWarps * 32, 0, st>>>(a);
+    const bool d32 = a.dout_dtype == XFS_F32;
+#define XFS_MID_BWD(T, TDO) ss2d_mid_bwd_kernel<T, TDO><<<grid, kMidWarps * 32, 0, st>>>(a)
+    if (a.dtype == XFS_F32) XFS_MID_BWD(float, float);
+    else if (a.dtype == XFS_BF16) { if (d32) XFS_MID_BWD(__nv_bfloat16, float); else XFS_MID_BWD(__nv_bfloat16, __nv_bfloat16); }
+    else { if (d32) XFS_MID_BWD(__half, float); else XFS_MID_BWD(__half, __half); }
+#undef XFS_MID_BWD
     return check_launch();
 }
 
