@@ -10,8 +10,9 @@
 //     reverses the lane order of the warp scan), and the column-major copy for routes 1 / 3 is one round trip through a
 //     1 KB per-warp shared-memory tile (__syncwarp only, no CTA barrier anywhere);
 //   * y of routes 0+2 and of routes 1+3 accumulate in registers, one transposition back at the end;
-//   * the four routes are straight-line code, so the compiler overlaps the loads and the element-wise phase of route k+1
-//     with the shuffle latency of route k.
+//   * every row the warp needs is staged global -> shared memory with cp.async at kernel start (one exposed memory round
+//     trip per warp instead of one per route, no registers held by loads in flight); the B / C rows are shared by the CTA,
+//     whose four warps work on four channels of one batch image.
 // Backward: same structure, x and dy held in both orders, du accumulated in registers, no checkpoints needed (h starts at 0).
 #include <initializer_list>
 
@@ -87,24 +88,56 @@ __device__ __forceinline__ void mid_store4(T* __restrict__ ptr, float a, float b
     }
 }
 
-// delta / B / C of one route in ADDRESS order plus its three parameters, exactly as loaded.  The loads of route k+1 are
-// issued (in program order) BEFORE route k is computed: each warp then pays one exposed memory round trip, not four.
+// ---- asynchronous staging ---------------------------------------------------------------------------------------------
+// Every row a warp needs (x, dy, its four delta rows, and -- shared by the CTA, whose four channels belong to one batch
+// image -- the B and C rows of the four routes) is copied global -> shared memory with cp.async at kernel start, in address
+// order, one granule of 4 elements per lane and half row.  The warp then pays ONE exposed memory round trip for its whole
+// life instead of one per route, and the copies cost no registers.
+constexpr int kMidRow = 256;             // elements per staged row
+
+__device__ __forceinline__ void cp_async_granule(void* smem_dst, const void* gsrc, int bytes) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    if (bytes == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc));
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;" ::);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+template <typename T>
+__device__ __forceinline__ void mid_copy_row(T* __restrict__ srow, const T* __restrict__ grow, const MidLane& m) {
+    if (m.ok0) cp_async_granule(srow + m.p0, grow + m.p0, 4 * (int)sizeof(T));
+    if (m.ok1) cp_async_granule(srow + m.p0 + 4, grow + m.p0 + 4, 4 * (int)sizeof(T));
+}
+// two granules of a staged row at element offsets g0, g1
+template <typename T>
+__device__ __forceinline__ void mid_lds8(const T* __restrict__ srow, int g0, int g1, float (&v)[8]) {
+    if constexpr (sizeof(T) == 4) {
+        const float4 a = *reinterpret_cast<const float4*>(srow + g0), b = *reinterpret_cast<const float4*>(srow + g1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+        const uint2 a = *reinterpret_cast<const uint2*>(srow + g0), b = *reinterpret_cast<const uint2*>(srow + g1);
+        const T* ea = reinterpret_cast<const T*>(&a);
+        const T* eb = reinterpret_cast<const T*>(&b);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[i] = Elem<T>::to_f(ea[i]); v[4 + i] = Elem<T>::to_f(eb[i]); }
+    }
+}
+
+// delta / B / C of one route in ADDRESS order plus its three parameters
 struct MidLoads {
     float dt[8], B[8], C[8];
     float bias, Dd, A;
 };
 
 template <bool kRev, typename T>
-__device__ __forceinline__ void mid_issue(MidLoads& r, const T* __restrict__ dt_row, const T* __restrict__ Brow,
-                                          const T* __restrict__ Crow, const float* __restrict__ A, const float* __restrict__ Ds,
-                                          const float* __restrict__ dbias, int kd, const MidLane& m) {
+__device__ __forceinline__ void mid_fetch(MidLoads& r, const T* __restrict__ dt_srow, const T* __restrict__ B_srow,
+                                          const T* __restrict__ C_srow, float bias, float Dd, float A, const MidLane& m) {
     const int g0 = kRev ? m.g0r : m.g0f, g1 = kRev ? m.g1r : m.g1f;
-    mid_load8<T>(dt_row, g0, g1, r.dt);
-    mid_load8<T>(Brow, g0, g1, r.B);
-    mid_load8<T>(Crow, g0, g1, r.C);
-    r.bias = dbias ? __ldg(dbias + kd) : 0.0f;
-    r.Dd = Ds ? __ldg(Ds + kd) : 0.0f;
-    r.A = __ldg(A + kd);
+    mid_lds8<T>(dt_srow, g0, g1, r.dt);
+    mid_lds8<T>(B_srow, g0, g1, r.B);
+    mid_lds8<T>(C_srow, g0, g1, r.C);
+    r.bias = bias; r.Dd = Dd; r.A = A;
 }
 
 // ---- one route of the forward, everything in registers ----------------------------------------------------------------
@@ -160,48 +193,69 @@ __device__ __forceinline__ void mid_route_fwd(const xfs_ss2d_fwd_args& p, const 
 }
 
 template <typename T, typename TO>
-__global__ void __launch_bounds__(kMidWarps * 32, 4)
+__global__ void __launch_bounds__(kMidWarps * 32, 6)
 ss2d_mid_fwd_kernel(const xfs_ss2d_fwd_args p) {
-    __shared__ __align__(16) float tiles[kMidWarps][kMidTile];
+    extern __shared__ __align__(16) unsigned char mid_smem[];
+    T* s_bc = reinterpret_cast<T*>(mid_smem);                  // [4 routes][B, C][kMidRow], shared by the CTA
+    T* s_dt = s_bc + 8 * kMidRow;                              // [4 warps][4 routes][kMidRow]
+    T* s_x = s_dt + 16 * kMidRow;                              // [4 warps][kMidRow]
+    float* s_tile = reinterpret_cast<float*>(s_x + 4 * kMidRow);   // [4 warps][kMidTile]
     const int H = (int)p.H, W = (int)p.W, L = H * W, D = (int)p.D;
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-    const int64_t chan = (int64_t)blockIdx.x * kMidWarps + wp;
-    if (chan >= p.batch * D) return;                 // warps are independent: no CTA barrier below
-    const int b = (int)(chan / D), d = (int)(chan - (int64_t)b * D);
-    float* tile = tiles[wp];
+    const int nd4 = (D + kMidWarps - 1) / kMidWarps;           // a CTA = 4 consecutive channels of ONE batch image
+    const int b = blockIdx.x / nd4, d = (blockIdx.x - b * nd4) * kMidWarps + wp;
+    const bool valid = d < D;
+    const int64_t chan = (int64_t)b * D + (valid ? d : 0);
+    float* tile = s_tile + wp * kMidTile;
     const MidLane m = mid_lane(lane, L);
 
-    const T* __restrict__ xrow = reinterpret_cast<const T*>(p.x) + chan * L;
     const T* __restrict__ delta = reinterpret_cast<const T*>(p.delta) + (int64_t)b * 4 * D * L;
-    const T* __restrict__ Bs = reinterpret_cast<const T*>(p.Bs) + (int64_t)b * 4 * L;
-    const T* __restrict__ Cs = reinterpret_cast<const T*>(p.Cs) + (int64_t)b * 4 * L;
+    // warp wp stages the B and C rows of route wp for the whole CTA, and its own x and delta rows
+    mid_copy_row<T>(s_bc + (2 * wp) * kMidRow, reinterpret_cast<const T*>(p.Bs) + ((int64_t)b * 4 + wp) * L, m);
+    mid_copy_row<T>(s_bc + (2 * wp + 1) * kMidRow, reinterpret_cast<const T*>(p.Cs) + ((int64_t)b * 4 + wp) * L, m);
+    float bias[4], Dd[4], Ak[4];
+    if (valid) {
+        mid_copy_row<T>(s_x + wp * kMidRow, reinterpret_cast<const T*>(p.x) + chan * L, m);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            mid_copy_row<T>(s_dt + (wp * 4 + k) * kMidRow, delta + (int64_t)(k * D + d) * L, m);
+            bias[k] = p.delta_bias ? __ldg(p.delta_bias + k * D + d) : 0.0f;
+            Dd[k] = p.Ds ? __ldg(p.Ds + k * D + d) : 0.0f;
+            Ak[k] = __ldg(p.A + k * D + d);
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();                     // the only CTA barrier: the shared B / C rows
+    if (!valid) return;
+
     float* st = p.states ? p.states + (int64_t)b * 4 * D : nullptr;       // (B, 4D, 1, 1)
-#define XFS_MID_ISSUE(R, K, REV)                                                                                                      \
-    mid_issue<REV, T>(R, delta + (int64_t)((K) * D + d) * L, Bs + (K) * L, Cs + (K) * L, p.A, p.Ds, p.delta_bias, (K) * D + d, m)
-    // every load the first two routes need is issued before the first loaded value is touched (in-order issue: the warp
-    // stalls at the first use, and whatever has not been issued by then waits behind it)
-    MidLoads ra, rb;
     float u[8], uT[8];
-    XFS_MID_ISSUE(ra, 0, false);
-    mid_load8<T>(xrow, m.g0f, m.g1f, u);
-    XFS_MID_ISSUE(rb, 2, true);
+    mid_lds8<T>(s_x + wp * kMidRow, m.g0f, m.g1f, u);
 #pragma unroll
     for (int i = 0; i < 8; ++i)
         if (m.p0 + i >= L) u[i] = 0.0f;
+    {
+        int gat[8];                                  // spatial index of column-major positions p0 .. p0+7 (q = w*H + h -> h*W + w)
+        mid_transposed_index(m.p0, W, H, L, gat);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) uT[i] = (m.p0 + i < L) ? Elem<T>::to_f(s_x[wp * kMidRow + gat[i]]) : 0.0f;
+    }
     float yN[8], yT[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { yN[i] = 0.0f; yT[i] = 0.0f; }
-    int gat[8];                                      // spatial index of column-major positions p0 .. p0+7 (q = w*H + h -> h*W + w)
-    mid_transposed_index(m.p0, W, H, L, gat);
-    mid_transpose(tile, u, uT, gat, m.p0);
+#define XFS_MID_FETCH(R, K, REV)                                                                                                     \
+    mid_fetch<REV, T>(R, s_dt + (wp * 4 + (K)) * kMidRow, s_bc + (2 * (K)) * kMidRow, s_bc + (2 * (K) + 1) * kMidRow, bias[K], Dd[K], Ak[K], m)
+    MidLoads r;
     // accumulation order of the reference merge: (y0 + y2) + (y1 + y3)
-    mid_route_fwd<false>(p, ra, m, L, lane, u, yN, st ? st + 0 * D + d : nullptr);
-    XFS_MID_ISSUE(ra, 1, false);
-    mid_route_fwd<true>(p, rb, m, L, lane, u, yN, st ? st + 2 * D + d : nullptr);
-    XFS_MID_ISSUE(rb, 3, true);
-    mid_route_fwd<false>(p, ra, m, L, lane, uT, yT, st ? st + 1 * D + d : nullptr);
-    mid_route_fwd<true>(p, rb, m, L, lane, uT, yT, st ? st + 3 * D + d : nullptr);
-#undef XFS_MID_ISSUE
+    XFS_MID_FETCH(r, 0, false);
+    mid_route_fwd<false>(p, r, m, L, lane, u, yN, st ? st + 0 * D + d : nullptr);
+    XFS_MID_FETCH(r, 2, true);
+    mid_route_fwd<true>(p, r, m, L, lane, u, yN, st ? st + 2 * D + d : nullptr);
+    XFS_MID_FETCH(r, 1, false);
+    mid_route_fwd<false>(p, r, m, L, lane, uT, yT, st ? st + 1 * D + d : nullptr);
+    XFS_MID_FETCH(r, 3, true);
+    mid_route_fwd<true>(p, r, m, L, lane, uT, yT, st ? st + 3 * D + d : nullptr);
+#undef XFS_MID_FETCH
 
     // y[p] = yN[p] + yT[column-major index of p]
     int sc[8];                                       // column-major index of spatial positions p0 .. p0+7
@@ -308,55 +362,80 @@ __device__ __forceinline__ void mid_route_bwd(const xfs_ss2d_bwd_args& p, const 
 template <typename T, typename TDO>
 __global__ void __launch_bounds__(kMidWarps * 32, 3)
 ss2d_mid_bwd_kernel(const xfs_ss2d_bwd_args p) {
-    __shared__ __align__(16) float tiles[kMidWarps][kMidTile];
+    extern __shared__ __align__(16) unsigned char mid_smem[];
+    T* s_bc = reinterpret_cast<T*>(mid_smem);                  // [4 routes][B, C][kMidRow], shared by the CTA
+    T* s_dt = s_bc + 8 * kMidRow;                              // [4 warps][4 routes][kMidRow]
+    T* s_x = s_dt + 16 * kMidRow;                              // [4 warps][kMidRow]
+    TDO* s_dy = reinterpret_cast<TDO*>(s_x + 4 * kMidRow);     // [4 warps][kMidRow]
+    float* s_tile = reinterpret_cast<float*>(s_dy + 4 * kMidRow);  // [4 warps][kMidTile]
     const int H = (int)p.H, W = (int)p.W, L = H * W, D = (int)p.D;
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
-    const int64_t chan = (int64_t)blockIdx.x * kMidWarps + wp;
-    if (chan >= p.batch * D) return;
-    const int b = (int)(chan / D), d = (int)(chan - (int64_t)b * D);
-    float* tile = tiles[wp];
+    const int nd4 = (D + kMidWarps - 1) / kMidWarps;
+    const int b = blockIdx.x / nd4, d = (blockIdx.x - b * nd4) * kMidWarps + wp;
+    const bool valid = d < D;
+    const int64_t chan = (int64_t)b * D + (valid ? d : 0);
+    float* tile = s_tile + wp * kMidTile;
     const MidLane m = mid_lane(lane, L);
 
     const T* __restrict__ delta = reinterpret_cast<const T*>(p.delta) + (int64_t)b * 4 * D * L;
     T* __restrict__ ddelta = reinterpret_cast<T*>(p.ddelta) + (int64_t)b * 4 * D * L;
-    const T* __restrict__ Bs = reinterpret_cast<const T*>(p.Bs) + (int64_t)b * 4 * L;
-    const T* __restrict__ Cs = reinterpret_cast<const T*>(p.Cs) + (int64_t)b * 4 * L;
     const int rep = p.acc_replicas > 1 ? d % p.acc_replicas : 0;        // accumulator replica of this channel (see xfscan.h)
     float* __restrict__ dBs = p.dBs + ((int64_t)rep * p.batch + b) * 4 * L;
     float* __restrict__ dCs = p.dCs + ((int64_t)rep * p.batch + b) * 4 * L;
-#define XFS_MID_ISSUE(R, K, REV)                                                                                                      \
-    mid_issue<REV, T>(R, delta + (int64_t)((K) * D + d) * L, Bs + (K) * L, Cs + (K) * L, p.A, p.Ds, p.delta_bias, (K) * D + d, m)
+    mid_copy_row<T>(s_bc + (2 * wp) * kMidRow, reinterpret_cast<const T*>(p.Bs) + ((int64_t)b * 4 + wp) * L, m);
+    mid_copy_row<T>(s_bc + (2 * wp + 1) * kMidRow, reinterpret_cast<const T*>(p.Cs) + ((int64_t)b * 4 + wp) * L, m);
+    float bias[4], Dd[4], Ak[4];
+    if (valid) {
+        mid_copy_row<T>(s_x + wp * kMidRow, reinterpret_cast<const T*>(p.x) + chan * L, m);
+        mid_copy_row<TDO>(s_dy + wp * kMidRow, reinterpret_cast<const TDO*>(p.dy) + chan * L, m);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            mid_copy_row<T>(s_dt + (wp * 4 + k) * kMidRow, delta + (int64_t)(k * D + d) * L, m);
+            bias[k] = p.delta_bias ? __ldg(p.delta_bias + k * D + d) : 0.0f;
+            Dd[k] = p.Ds ? __ldg(p.Ds + k * D + d) : 0.0f;
+            Ak[k] = __ldg(p.A + k * D + d);
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    if (!valid) return;
+
+#define XFS_MID_FETCH(R, K, REV)                                                                                                     \
+    mid_fetch<REV, T>(R, s_dt + (wp * 4 + (K)) * kMidRow, s_bc + (2 * (K)) * kMidRow, s_bc + (2 * (K) + 1) * kMidRow, bias[K], Dd[K], Ak[K], m)
 #define XFS_MID_ROUTE(R, K, REV, U, DY, DU)                                                                                           \
     mid_route_bwd<REV, T>(p, R, ddelta + (int64_t)((K) * D + d) * L, dBs + (K) * L, dCs + (K) * L, m, L, lane, U, DY, DU, pg[K])
-    MidLoads ra, rb;
+    MidLoads r;
     float u[8], dy[8], duN[8], pg[4][3];
-    XFS_MID_ISSUE(ra, 0, false);         // everything routes 0 and 2 need, issued before the first use (see the forward)
-    mid_load8<T>(reinterpret_cast<const T*>(p.x) + chan * L, m.g0f, m.g1f, u);
-    mid_load8<TDO>(reinterpret_cast<const TDO*>(p.dy) + chan * L, m.g0f, m.g1f, dy);
-    XFS_MID_ISSUE(rb, 2, true);
+    mid_lds8<T>(s_x + wp * kMidRow, m.g0f, m.g1f, u);
+    mid_lds8<TDO>(s_dy + wp * kMidRow, m.g0f, m.g1f, dy);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         duN[i] = 0.0f;
         if (m.p0 + i >= L) { u[i] = 0.0f; dy[i] = 0.0f; }
     }
-    XFS_MID_ROUTE(ra, 0, false, u, dy, duN);
-    XFS_MID_ISSUE(ra, 1, false);
-    XFS_MID_ROUTE(rb, 2, true, u, dy, duN);
-    // the row-major copies are done: turn them into the column-major ones for routes 1 / 3
+    XFS_MID_FETCH(r, 0, false);
+    XFS_MID_ROUTE(r, 0, false, u, dy, duN);
+    XFS_MID_FETCH(r, 2, true);
+    XFS_MID_ROUTE(r, 2, true, u, dy, duN);
+    // the row-major copies are done: the column-major ones for routes 1 / 3 come straight from the staged rows
     float uT[8], dyT[8], duT[8];
     {
         int gat[8];
         mid_transposed_index(m.p0, W, H, L, gat);
-        mid_transpose(tile, u, uT, gat, m.p0);
-        mid_transpose(tile, dy, dyT, gat, m.p0);
-    }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) duT[i] = 0.0f;
-    XFS_MID_ISSUE(rb, 3, true);
-    XFS_MID_ROUTE(ra, 1, false, uT, dyT, duT);
-    XFS_MID_ROUTE(rb, 3, true, uT, dyT, duT);
+        for (int i = 0; i < 8; ++i) {
+            const bool in = m.p0 + i < L;
+            uT[i] = in ? Elem<T>::to_f(s_x[wp * kMidRow + gat[i]]) : 0.0f;
+            dyT[i] = in ? Elem<TDO>::to_f(s_dy[wp * kMidRow + gat[i]]) : 0.0f;
+            duT[i] = 0.0f;
+        }
+    }
+    XFS_MID_FETCH(r, 1, false);
+    XFS_MID_ROUTE(r, 1, false, uT, dyT, duT);
+    XFS_MID_FETCH(r, 3, true);
+    XFS_MID_ROUTE(r, 3, true, uT, dyT, duT);
 #undef XFS_MID_ROUTE
-#undef XFS_MID_ISSUE
+#undef XFS_MID_FETCH
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
@@ -398,10 +477,11 @@ static bool mid_ptrs_ok(std::initializer_list<const void*> ps, size_t align) {
 int launch_ss2d_mid_fwd(const xfs_ss2d_fwd_args& a, cudaStream_t st) {
     const size_t al = a.dtype == XFS_F32 ? 16 : 8;
     if (!mid_ptrs_ok({a.x, a.delta, a.Bs, a.Cs}, al) || !mid_ptrs_ok({a.y}, a.out_dtype == XFS_F32 ? 16 : 8)) return XFS_ERR_UNSUPPORTED;
-    const int64_t chans = a.batch * a.D;
-    const unsigned grid = (unsigned)((chans + kMidWarps - 1) / kMidWarps);
+    const unsigned grid = (unsigned)(a.batch * ((a.D + kMidWarps - 1) / kMidWarps));
     const bool o32 = a.out_dtype == XFS_F32;
-#define XFS_MID_FWD(T, TO) ss2d_mid_fwd_kernel<T, TO><<<grid, kMidWarps * 32, 0, st>>>(a)
+    const size_t es = a.dtype == XFS_F32 ? 4 : 2;
+    const size_t smem = 28 * kMidRow * es + kMidWarps * kMidTile * sizeof(float);
+#define XFS_MID_FWD(T, TO) ss2d_mid_fwd_kernel<T, TO><<<grid, kMidWarps * 32, smem, st>>>(a)
     if (a.dtype == XFS_F32) XFS_MID_FWD(float, float);
     else if (a.dtype == XFS_BF16) { if (o32) XFS_MID_FWD(__nv_bfloat16, float); else XFS_MID_FWD(__nv_bfloat16, __nv_bfloat16); }
     else { if (o32) XFS_MID_FWD(__half, float); else XFS_MID_FWD(__half, __half); }
@@ -414,10 +494,11 @@ int launch_ss2d_mid_bwd(const xfs_ss2d_bwd_args& a, cudaStream_t st) {
     if (!mid_ptrs_ok({a.x, a.delta, a.Bs, a.Cs, a.dx, a.ddelta}, al) || !mid_ptrs_ok({a.dy}, a.dout_dtype == XFS_F32 ? 16 : 8) ||
         !mid_ptrs_ok({a.dBs, a.dCs}, 16))
         return XFS_ERR_UNSUPPORTED;
-    const int64_t chans = a.batch * a.D;
-    const unsigned grid = (unsigned)((chans + kMidWarps - 1) / kMidWarps);
+    const unsigned grid = (unsigned)(a.batch * ((a.D + kMidWarps - 1) / kMidWarps));
     const bool d32 = a.dout_dtype == XFS_F32;
-#define XFS_MID_BWD(T, TDO) ss2d_mid_bwd_kernel<T, TDO><<<grid, kMidWarps * 32, 0, st>>>(a)
+    const size_t es = a.dtype == XFS_F32 ? 4 : 2;
+    const size_t smem = 28 * kMidRow * es + 4 * kMidRow * (d32 ? 4 : 2) + kMidWarps * kMidTile * sizeof(float);
+#define XFS_MID_BWD(T, TDO) ss2d_mid_bwd_kernel<T, TDO><<<grid, kMidWarps * 32, smem, st>>>(a)
     if (a.dtype == XFS_F32) XFS_MID_BWD(float, float);
     else if (a.dtype == XFS_BF16) { if (d32) XFS_MID_BWD(__nv_bfloat16, float); else XFS_MID_BWD(__nv_bfloat16, __nv_bfloat16); }
     else { if (d32) XFS_MID_BWD(__half, float); else XFS_MID_BWD(__half, __half); }
