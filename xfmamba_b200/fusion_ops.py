@@ -156,10 +156,11 @@ def ss2d_acc_replicas(D, L):
     return max(1, min(R, int(D)))
 
 
-def ss2d_bwd_raw(x, delta, A, Bs, Cs, Ds, delta_bias, dy, states, delta_softplus=True, out=None, zero=True):
+def ss2d_bwd_raw(x, delta, A, Bs, Cs, Ds, delta_bias, dy, states, delta_softplus=True, out=None, zero=True, reduce=True):
     """One launch of the fused backward kernel (C ABI ``xfs_ss2d_bwd``).  Returns (dx, ddelta, dA, dBs, dCs, dDs,
     ddelta_bias) with dBs/dCs fp32.  ``out`` may carry the 7 buffers for reuse; its dBs/dCs entries may be replicated
-    accumulators (R, B, 4, N, L) (see ``ss2d_acc_replicas``), which are summed over R here.  The accumulated buffers are
+    accumulators (R, B, 4, N, L) (see ``ss2d_acc_replicas``), which are summed over R here (``reduce=False``: returned as they
+    are, for callers that time the kernel alone).  The accumulated buffers are
     zero-filled here (stream-ordered memsets) unless ``zero=False`` (caller already did), as the reference host code does
     (selective_scan.cpp:331-337)."""
     Bsz, D, H, W = x.shape
@@ -186,7 +187,7 @@ def ss2d_bwd_raw(x, delta, A, Bs, Cs, Ds, delta_bias, dy, states, delta_softplus
         with torch.cuda.device(dev):
             rc = _lib.lib().xfs_ss2d_bwd(args, _lib.stream(dev))
         _lib.check(rc, "ss2d_bwd")
-    if dBs.dim() == 5:
+    if dBs.dim() == 5 and reduce:
         dBs, dCs = dBs.sum(0), dCs.sum(0)
     return dx, ddelta, dA, dBs, dCs, dDs, dbias
 
