@@ -75,10 +75,11 @@ def selective_scan_fwd_raw(u, delta, A, B, C, D, delta_bias, delta_softplus, ofl
     return out, states, (u, delta, A, B, C, D, delta_bias)
 
 
-def _acc_replicas(channels_per_group, L):
+def _acc_replicas(channels_per_group, L, batch):
     """copies of the dB/dC accumulators (``xfs_scan_bwd_args.acc_replicas``); short rows go through the kernel that already
-    sums 128 rows per CTA in shared memory"""
-    if L <= 64 or channels_per_group < 8:
+    sums 128 rows per CTA in shared memory, and with a large batch the batch-fastest walk of the kernel keeps the channels
+    of one image apart (see fusion_ops.ss2d_acc_replicas)"""
+    if L <= 64 or channels_per_group < 8 or batch >= 32:
         return 1
     return min(4 if L >= 2048 else 8, channels_per_group)
 
@@ -96,7 +97,7 @@ def selective_scan_bwd_raw(u, delta, A, B, C, D, delta_bias, dout, states, delta
     ddelta = torch.empty_like(delta)
     dA = torch.zeros_like(A)
     # dB / dC accumulators in R copies (channel d -> copy d % R): all dim/G channels of a group add into the same L2 lines
-    R = _acc_replicas(dim // G, L)
+    R = _acc_replicas(dim // G, L, batch)
     acc_shape = tuple(B.shape) if R == 1 else (R,) + tuple(B.shape)
     dB = torch.zeros(acc_shape, dtype=torch.float32, device=dev)
     dC = torch.zeros(acc_shape, dtype=torch.float32, device=dev)

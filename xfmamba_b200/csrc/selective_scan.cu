@@ -100,9 +100,12 @@ sscan_bwd_kernel(const xfs_scan_bwd_args p) {
     __shared__ float s_q[kWarpsPerCta][kMaxState];    // reverse carry per state
     __shared__ float s_dA[kWarpsPerCta][kMaxState];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t seq = (int64_t)blockIdx.x * kWarpsPerCta + wib;
-    if (seq >= p.batch * p.dim) return;
-    const int64_t b = seq / p.dim, d = seq % p.dim;
+    const int64_t work = (int64_t)blockIdx.x * kWarpsPerCta + wib;
+    if (work >= p.batch * p.dim) return;
+    // batch index fastest: the warps resident at any moment then belong to many batch images, and few of them add into
+    // the same dB / dC rows (shared by all channels of one image and group) at the same time
+    const int64_t b = work % p.batch, d = work / p.batch;
+    const int64_t seq = b * p.dim + d;
     const int64_t L = p.seqlen, N = p.dstate;
     const int64_t g = d / (p.dim / p.ngroups);
     const int64_t nchunks = (L + kChunk - 1) / kChunk;

@@ -29,8 +29,10 @@ ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
     const int D = (int)p.D;
     const int N = (kN == 1) ? 1 : (int)p.N;
     const int groups = (D + kCh - 1) / kCh;
-    const int b = blockIdx.x / groups;
-    const int d0 = (blockIdx.x - b * groups) * kCh;
+    // batch index fastest: the CTAs resident at any moment then belong to as many different batch images as possible, so
+    // few of them add into the same dB / dC rows at the same time (those rows are shared by all channels of one image)
+    const int b = blockIdx.x % (int)p.batch;
+    const int d0 = (blockIdx.x / (int)p.batch) * kCh;
     const int tid = threadIdx.x, lane = tid & 31, k = tid >> 5;
     const bool transposed = k & 1;
     bool valid[kCh];

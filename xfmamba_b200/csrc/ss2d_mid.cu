@@ -371,7 +371,8 @@ ss2d_mid_bwd_kernel(const xfs_ss2d_bwd_args p) {
     const int H = (int)p.H, W = (int)p.W, L = H * W, D = (int)p.D;
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
     const int nd4 = (D + kMidWarps - 1) / kMidWarps;
-    const int b = blockIdx.x / nd4, d = (blockIdx.x - b * nd4) * kMidWarps + wp;
+    // batch index fastest (see ss2d_bwd.cu): concurrent CTAs spread over the batch images, not over the channels of one
+    const int b = blockIdx.x % (int)p.batch, d = (blockIdx.x / (int)p.batch) * kMidWarps + wp;
     const bool valid = d < D;
     const int64_t chan = (int64_t)b * D + (valid ? d : 0);
     float* tile = s_tile + wp * kMidTile;

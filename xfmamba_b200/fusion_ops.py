@@ -142,17 +142,19 @@ def ss2d_fwd_raw(x, delta, A, Bs, Cs, Ds, delta_bias, delta_softplus=True, out_d
     return y, states
 
 
-def ss2d_acc_replicas(D, L):
-    """Replicas of the dBs/dCs accumulators (``xfs_ss2d_bwd_args.acc_replicas``): every channel of a batch image adds into
-    the same L2 lines at the same time; spreading the D channels over R copies removes that serialisation."""
+def ss2d_acc_replicas(D, L, batch=1):
+    """Replicas of the dBs/dCs accumulators (``xfs_ss2d_bwd_args.acc_replicas``).  Every channel of a batch image adds into the
+    same L2 lines; the backward kernels already walk the batch index fastest, so with a large batch the CTAs resident at one
+    time belong to different images and no replica is needed (measured: R = 1 is fastest from batch 64 on).  Small batches
+    bring the channels of one image back together, and spreading them over R copies removes the serialisation."""
     env = os.environ.get("XFS_ACC_REPLICAS")
     if env:
         return max(1, min(int(env), int(D), 64))
-    # measured on B200 (profiles/r01_shape_sweep.md): 4 copies recover most of the loss at 56x56 (more copies cost more in
-    # zero-fills and in the final sum than they save), short rows with many channels want 8-16
-    if L <= 64:
-        return 1                      # the short-sequence kernel already sums 32 channels per CTA in shared memory (measured: no gain)
+    if L <= 64 or batch >= 32:
+        return 1                      # L <= 64: the short-sequence kernel sums 32 channels per CTA in shared memory
     R = 4 if L >= 2048 else (8 if D < 1024 else 16)
+    if batch >= 8:
+        R //= 2
     return max(1, min(R, int(D)))
 
 
@@ -166,7 +168,7 @@ def ss2d_bwd_raw(x, delta, A, Bs, Cs, Ds, delta_bias, dy, states, delta_softplus
     Bsz, D, H, W = x.shape
     N, dev = Bs.shape[2], x.device
     if out is None:
-        R = ss2d_acc_replicas(D, H * W)
+        R = ss2d_acc_replicas(D, H * W, Bsz)
         acc_shape = tuple(Bs.shape) if R == 1 else (R,) + tuple(Bs.shape)
         out = (torch.empty_like(x), torch.empty_like(delta), torch.empty_like(A),
                torch.empty(acc_shape, dtype=torch.float32, device=dev), torch.empty(acc_shape, dtype=torch.float32, device=dev),
