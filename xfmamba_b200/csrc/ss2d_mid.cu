@@ -8,7 +8,7 @@
 // Here ONE WARP owns a channel image and runs its four routes back to back:
 //   * lane i holds spatial positions 8i .. 8i+7 in registers -- that IS the scan order of routes 0 / 2 (the flip only
 //     reverses the lane order of the warp scan), and the column-major copy for routes 1 / 3 is one round trip through a
-//     1 KB per-warp shared-memory tile (__syncwarp only, no CTA barrier anywhere);
+//     the warp's staged rows in shared memory (__syncwarp only);
 //   * y of routes 0+2 and of routes 1+3 accumulate in registers, one transposition back at the end;
 //   * every row the warp needs is staged global -> shared memory with cp.async at kernel start (one exposed memory round
 //     trip per warp instead of one per route, no registers held by loads in flight); the B / C rows are shared by the CTA,
@@ -63,19 +63,7 @@ __device__ __forceinline__ void mid_transpose(float* tile, const float (&src)[8]
     for (int i = 0; i < 8; ++i) dst[i] = tile[gather[i]];
 }
 
-// two granules of 4 elements (16 bytes fp32, 8 bytes bf16 / f16) at element offsets g0, g1 of a row whose start is granule aligned
-template <typename T>
-__device__ __forceinline__ void mid_load8(const T* __restrict__ row, int g0, int g1, float (&v)[8]) {
-    if constexpr (sizeof(T) == 4) {
-        load8_at<T>(row, g0, g1, v);
-    } else {
-        const uint2 a = __ldg(reinterpret_cast<const uint2*>(row + g0)), b = __ldg(reinterpret_cast<const uint2*>(row + g1));
-        const T* ea = reinterpret_cast<const T*>(&a);
-        const T* eb = reinterpret_cast<const T*>(&b);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { v[i] = Elem<T>::to_f(ea[i]); v[4 + i] = Elem<T>::to_f(eb[i]); }
-    }
-}
+// four consecutive elements (16 bytes fp32, 8 bytes bf16 / f16) to a granule-aligned address
 template <typename T>
 __device__ __forceinline__ void mid_store4(T* __restrict__ ptr, float a, float b, float c, float d) {
     if constexpr (sizeof(T) == 4) {
