@@ -481,6 +481,7 @@ def test_dwconv3x3_rejects_cpu_tensors():
 @pytest.mark.parametrize("B,K,R,D,L,sliced", [
     (2, 4, 6, 192, 3136, True), (3, 4, 24, 70, 196, True), (2, 4, 48, 33, 49, True), (2, 2, 64, 40, 256, False),
     (1, 4, 1, 5, 7, False), (2, 4, 12, 384, 784, True), (1, 4, 8, 16, 1023, False),
+    (3, 4, 8, 20, 49, True), (5, 2, 16, 9, 100, False),      # short rows: several images per CTA, last group partial
 ])
 def test_dt_proj_fwd_bwd_vs_oracle(B, K, R, D, L, sliced):
     from xfmamba_b200.proj import dt_proj
