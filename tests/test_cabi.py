@@ -121,3 +121,20 @@ def test_operator_signatures_match_reference():
     from xfmamba_b200 import csms6s, csm_triton
     assert csms6s.CrossScan is xf.CrossScanF and csms6s.CrossMerge is xf.CrossMergeF
     assert csm_triton.cross_scan_fn is xf.cross_scan_fn
+
+
+def test_accumulator_replica_heuristics(monkeypatch):
+    """host logic only: replicas are never more than channels, 1 for large batches and short rows, overridable"""
+    from xfmamba_b200 import csms6s, fusion_ops
+    monkeypatch.delenv("XFS_ACC_REPLICAS", raising=False)
+    assert fusion_ops.ss2d_acc_replicas(192, 3136, 64) == 1
+    assert fusion_ops.ss2d_acc_replicas(192, 3136, 2) == 4
+    assert fusion_ops.ss2d_acc_replicas(1024, 196, 2) == 16
+    assert fusion_ops.ss2d_acc_replicas(1024, 196, 16) == 8
+    assert fusion_ops.ss2d_acc_replicas(2048, 49, 2) == 1
+    assert fusion_ops.ss2d_acc_replicas(3, 196, 1) == 3
+    monkeypatch.setenv("XFS_ACC_REPLICAS", "5")
+    assert fusion_ops.ss2d_acc_replicas(192, 3136, 64) == 5
+    assert csms6s._acc_replicas(192, 3136, 64) == 1
+    assert csms6s._acc_replicas(192, 3136, 4) == 4
+    assert csms6s._acc_replicas(4, 3136, 4) == 1
