@@ -91,6 +91,14 @@ ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
 
         const T* pf_row = (kN != 1 || kCh != 1 || kSingle || lane >= 24) ? nullptr : (lane < 8) ? dt_row[0] : (lane < 16) ? Bk : Ck;
 
+        // Only the LAST chunk (spatial positions >= L) has 16-byte granules outside the rows: its per-lane offsets and
+        // validity flags are computed once, so every other chunk loads, stores and reduces without range checks (kFast)
+        const int p0_last = (nch - 1) * kChunk + lane * kItems;
+        const int l0_last = rev ? L - 8 - p0_last : p0_last;
+        const bool okA_last = l0_last >= 0 && l0_last + 4 <= L, okB_last = l0_last + 4 >= 0 && l0_last + 8 <= L;
+        const int g0_last = okA_last ? l0_last : 0, g1_last = okB_last ? l0_last + 4 : 0;
+        constexpr bool kVec4 = kFast && Elem<T>::kVec == 4;
+
         auto load_chunk = [&](int step, BwdChunk<kN, kCh>& c) __attribute__((always_inline)) {
             const int j = rev ? step : (nch - 1 - step);
             if (kN == 1 && kCh == 1 && !kSingle) {
@@ -103,14 +111,20 @@ ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
             const int p0 = j * kChunk + lane * kItems;
             const int l0 = rev ? L - 8 - p0 : p0;
             const int jprev = rev ? j + 1 : j - 1;           // chunk the forward walked just before this one
+            const bool last = (j == nch - 1);
+            const int g0 = last ? g0_last : l0, g1 = last ? g1_last : l0 + 4;
 #pragma unroll
             for (int ch = 0; ch < kCh; ++ch) {
-                row_load8<T, kFast>(dt_row[ch], l0, L, vin, c.dt[ch]);
+                if constexpr (kVec4) load8_at<T>(dt_row[ch], g0, g1, c.dt[ch]);
+                else row_load8<T, kFast>(dt_row[ch], l0, L, vin, c.dt[ch]);
                 if (kN == 1) c.hstart[ch] = (jprev >= 0 && jprev < nch) ? st_row[ch][jprev] : 0.0f;
             }
             if (kN == 1) {
-                row_load8<T, kFast>(Bk, l0, L, vin, c.B);
-                row_load8<T, kFast>(Ck, l0, L, vin, c.C);
+                if constexpr (kVec4) { load8_at<T>(Bk, g0, g1, c.B); load8_at<T>(Ck, g0, g1, c.C); }
+                else {
+                    row_load8<T, kFast>(Bk, l0, L, vin, c.B);
+                    row_load8<T, kFast>(Ck, l0, L, vin, c.C);
+                }
             }
         };
 
@@ -298,11 +312,12 @@ ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
                 float* dBrow = dBk + n * L;
                 float* dCrow = dCk + n * L;
                 if (vacc) {     // L % 4 == 0: each 16-byte granule is entirely inside or outside the row
-                    if (l0 >= 0 && l0 + 4 <= L) {
+                    const bool lastc = (j == nch - 1);
+                    if (!lastc || okA_last) {
                         red_add_v4(dBrow + l0, dBa[0], dBa[1], dBa[2], dBa[3]);
                         red_add_v4(dCrow + l0, dCa[0], dCa[1], dCa[2], dCa[3]);
                     }
-                    if (l0 + 4 >= 0 && l0 + 8 <= L) {
+                    if (!lastc || okB_last) {
                         red_add_v4(dBrow + l0 + 4, dBa[4], dBa[5], dBa[6], dBa[7]);
                         red_add_v4(dCrow + l0 + 4, dCa[4], dCa[5], dCa[6], dCa[7]);
                     }
@@ -332,7 +347,15 @@ ss2d_bwd_kernel(const xfs_ss2d_bwd_args p) {
                 if (kCh == 1 || valid[ch]) {
                     float dda[8];
                     to_pos<rev>(ddt, dda);
-                    row_store8<T, kFast>(ddt_row[ch], l0, L, vout, dda);
+                    if constexpr (kVec4) {
+                        const bool lastc = (j == nch - 1);
+                        if (!lastc || okA_last)
+                            stg16(ddt_row[ch] + l0, make_uint4(__float_as_uint(dda[0]), __float_as_uint(dda[1]), __float_as_uint(dda[2]), __float_as_uint(dda[3])));
+                        if (!lastc || okB_last)
+                            stg16(ddt_row[ch] + l0 + 4, make_uint4(__float_as_uint(dda[4]), __float_as_uint(dda[5]), __float_as_uint(dda[6]), __float_as_uint(dda[7])));
+                    } else {
+                        row_store8<T, kFast>(ddt_row[ch], l0, L, vout, dda);
+                    }
                 }
                 if (in_buf) {
                     if (!first_touch) {
