@@ -382,6 +382,72 @@ def test_ss2d_full_size_properties(xf):
     assert rel_err(n(y_rot), n(yf.flip(2))) < TOL32
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_ss2d_config2_shape_vs_oracle(xf, dtype):
+    """BASELINE config 2 at its exact per-image shape (D = 192, 56x56, N = 1, K = 4; 8 images) against the CPU oracle:
+    forward and all seven gradients, fp32 and bf16 inputs (fp32 out).  Also per-row relative checks of the delta-scale
+    quantities (a tensor-scale metric hides errors of small dt / ddelta values)."""
+    rng = np.random.default_rng(2)
+    Bsz, D, N, H, W = 8, 192, 1, 56, 56
+    c = _rand_ss2d(rng, Bsz, D, N, H, W)
+    if dtype != torch.float32:
+        for k in ("x", "delta", "Bs", "Cs"):
+            c[k] = t(c[k]).to(dtype).float().cpu().numpy()
+    tol = TOL32 if dtype == torch.float32 else TOL16
+    y, leaves = _run_ss2d(xf, c, dtype, True)
+    assert y.dtype == torch.float32
+    ref = oracle.ss2d_fwd(c["x"], c["delta"], c["A"], c["Bs"], c["Cs"], c["Ds"], c["delta_bias"], True, "f64")
+    assert rel_err(n(y), ref) < TOL32
+    grads = oracle.ss2d_bwd(c["x"], c["delta"], c["A"], c["Bs"], c["Cs"], c["Ds"], c["delta_bias"], c["dy"], True, "f64")
+    for k, gr in zip(SS2D_KEYS, grads):
+        assert rel_err(n(leaves[k].grad), gr) < tol, f"d{k}"
+    if dtype == torch.float32:      # row-wise: every (b, k*D + d) row of ddelta and every (b, d) row of y on its own scale
+        dd, ddr = n(leaves["delta"].grad), grads[1]
+        row = np.max(np.abs(dd - ddr), axis=-1) / np.maximum(np.max(np.abs(ddr), axis=-1), 1e-30)
+        assert float(row.max()) < 2e-4, float(row.max())
+        yy = n(y)
+        row = np.max(np.abs(yy - ref), axis=-1) / np.maximum(np.max(np.abs(ref), axis=-1), 1e-30)
+        assert float(row.max()) < 2e-4, float(row.max())
+
+
+@pytest.mark.parametrize("shape", [(1, 64, 1, 64, 64), (1, 64, 1, 128, 128), (2, 3, 1, 40, 44), (1, 2, 1, 20, 13), (1, 3, 1, 2, 130)])
+@pytest.mark.parametrize("model_like", [False, True])
+def test_ss2d_long_rows_vs_oracle(xf, shape, model_like):
+    """long-sequence path (512^2 inputs: stage-1 L = 16384, stage-2 L = 4096) and ragged multi-chunk shapes, whichever kernel
+    or composition serves them: forward and all gradients against the oracle.  model_like puts dt in [1e-3, 1e-1], where
+    softplus needs its small-argument branch."""
+    Bsz, D, N, H, W = shape
+    rng = np.random.default_rng(abs(hash(shape)) % 2**32)
+    c = _rand_ss2d(rng, Bsz, D, N, H, W, model_like)
+    y, leaves = _run_ss2d(xf, c)
+    ref = oracle.ss2d_fwd(c["x"], c["delta"], c["A"], c["Bs"], c["Cs"], c["Ds"], c["delta_bias"], True, "f64")
+    assert rel_err(n(y), ref) < TOL32
+    grads = oracle.ss2d_bwd(c["x"], c["delta"], c["A"], c["Bs"], c["Cs"], c["Ds"], c["delta_bias"], c["dy"], True, "f64")
+    for k, gr in zip(SS2D_KEYS, grads):
+        assert rel_err(n(leaves[k].grad), gr) < TOL32, f"d{k}"
+
+
+def test_ss2d_softplus_branches_mixed_in_one_chunk(xf):
+    """the TMA-fed kernels take a chunk-uniform shortcut when no element of a chunk needs the small-argument series or the
+    x > 20 identity of softplus (csrc/ss2d_ring.cuh); mix all three regimes inside single chunks and across chunks."""
+    rng = np.random.default_rng(17)
+    Bsz, D, N, H, W = 2, 4, 1, 24, 28
+    c = _rand_ss2d(rng, Bsz, D, N, H, W)
+    L = H * W
+    d = c["delta"]
+    d[:, :, 5::37] = -9.0 + rng.random(d[:, :, 5::37].shape, dtype=np.float32)         # e^x ~ 1e-4: series branch
+    d[:, :, 11::53] = 21.0 + 3 * rng.random(d[:, :, 11::53].shape, dtype=np.float32)   # x > 20: identity branch
+    d[0, 1, 300:560] = -12.0                                                            # a whole chunk of tiny dt
+    d[1, 2, :] = 0.25                                                                   # a whole row on the fast path
+    c["A"] = -0.01 * rng.random((4 * D, N), dtype=np.float32)                          # keep exp(dt A) away from 0 for dt ~ 24
+    y, leaves = _run_ss2d(xf, c)
+    ref = oracle.ss2d_fwd(c["x"], c["delta"], c["A"], c["Bs"], c["Cs"], c["Ds"], c["delta_bias"], True, "f64")
+    assert rel_err(n(y), ref) < TOL32
+    grads = oracle.ss2d_bwd(c["x"], c["delta"], c["A"], c["Bs"], c["Cs"], c["Ds"], c["delta_bias"], c["dy"], True, "f64")
+    for k, gr in zip(SS2D_KEYS, grads):
+        assert rel_err(n(leaves[k].grad), gr) < TOL32, f"d{k}"
+
+
 def test_ss2d_unfused_fallback_large_L(xf):
     """L too large for the fused working set -> the operator composes the stand-alone kernels (still CUDA)"""
     rng = np.random.default_rng(9)

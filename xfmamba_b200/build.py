@@ -19,8 +19,8 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 SO = PKG / "libxfscan.so"
 OBJ = PKG / "build"
-SOURCES = ["routes.cu", "selective_scan.cu", "ss2d_fwd.cu", "ss2d_bwd.cu", "ss2d_small.cu", "ss2d_mid.cu", "layernorm2d.cu", "dwconv.cu", "dtproj.cu", "capi.cu"]
-HEADERS = [CSRC / "xfscan_common.cuh", CSRC / "ss2d_tiles.cuh", CSRC / "ss2d_fused.cuh", PKG.parent / "include" / "xfscan.h"]
+SOURCES = ["routes.cu", "selective_scan.cu", "ss2d_fwd.cu", "ss2d_bwd.cu", "ss2d_ring_fwd.cu", "ss2d_small.cu", "ss2d_mid.cu", "layernorm2d.cu", "dwconv.cu", "dtproj.cu", "capi.cu"]
+HEADERS = [CSRC / "xfscan_common.cuh", CSRC / "ss2d_tiles.cuh", CSRC / "ss2d_fused.cuh", CSRC / "ss2d_ring.cuh", PKG.parent / "include" / "xfscan.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -17,6 +17,8 @@ int ss2d_supported(int64_t, int64_t, int64_t, int64_t, int, int);
 int ss2d_small_supported(int64_t, int64_t, int64_t);
 int launch_ss2d_small_fwd(const xfs_ss2d_fwd_args&, cudaStream_t);
 int launch_ss2d_small_bwd(const xfs_ss2d_bwd_args&, cudaStream_t);
+int ss2d_ring_fwd_supported(const xfs_ss2d_fwd_args&);
+int launch_ss2d_ring_fwd(const xfs_ss2d_fwd_args&, cudaStream_t);
 int ss2d_mid_supported(int64_t, int64_t, int64_t);
 int launch_ss2d_mid_fwd(const xfs_ss2d_fwd_args&, cudaStream_t);
 int launch_ss2d_mid_bwd(const xfs_ss2d_bwd_args&, cudaStream_t);
@@ -146,6 +148,7 @@ int xfs_ss2d_fwd(const xfs_ss2d_fwd_args* a, xfs_stream_t stream) {
         const int rc = launch_ss2d_mid_fwd(*a, (cudaStream_t)stream);
         if (rc != XFS_ERR_UNSUPPORTED) return rc;
     }
+    if (ss2d_ring_fwd_supported(*a)) return launch_ss2d_ring_fwd(*a, (cudaStream_t)stream);   // TMA-fed kernel (N = 1, fp32)
     if (!ss2d_supported(a->D, a->N, a->H, a->W, a->dtype, 0)) return XFS_ERR_UNSUPPORTED;
     return launch_ss2d_fwd(*a, (cudaStream_t)stream);
 }
