@@ -37,6 +37,12 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void pair_barrier_n(int pair, int nthreads) {   // all warps of a route pair (routes k and k+2)
+    asm volatile("bar.sync %0, %1;" ::"r"(pair + 1), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -64,6 +70,10 @@ __device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes
 __device__ __forceinline__ void bulk_red_add_f32(float* dst, uint32_t src, uint32_t bytes) {
     asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
                  : "memory");
+}
+// asynchronous L2 prefetch of a contiguous range (one instruction, no destination); 16-byte aligned, bytes % 16 == 0
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int kPending>
@@ -104,6 +114,13 @@ __device__ __forceinline__ float4 half_to(const f2 lo, const f2 hi) {
     return kFlip ? make_float4(hi.y, hi.x, lo.y, lo.x) : make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 
+// Swizzle of the column-major image copies.  ss2d_tiles.cuh XORs granule bit 0 as well, which is exactly the alternation
+// the A/B access order already provides -- combined they cancel and put lanes i and i+4 back on the same banks (measured:
+// 6 instead of 4 wavefronts per LDS.128/STS.128 on those buffers).  Here only granule bits 1-2 are XORed: the lane access
+// stays conflict free, the transposing 16-byte stores (granule stride H) spread over 4 bank groups (2-way).
+__device__ __forceinline__ int rswz_f4(int f) { return f ^ (((f >> 3) & 3) << 1); }
+__device__ __forceinline__ int rswz_pos(int p) { return (rswz_f4(p >> 2) << 2) | (p & 3); }
+
 // per-lane byte offsets (within a 256-position chunk) of the A and B granules
 struct LaneOffsets {
     uint32_t imgA, imgB;     // position-indexed image / accumulator buffers of this route's orientation
@@ -122,9 +139,8 @@ __device__ __forceinline__ LaneOffsets lane_offsets(int lane, bool rev, bool tra
         o.imgA = (uint32_t)(f + s) * 16u;
         o.imgB = (uint32_t)(f + 1 - s) * 16u;
     } else {                                     // column-major copy: XOR-swizzled granules (ss2d_tiles.cuh)
-        const int lo = f ^ ((f >> 3) & 7), hi = lo ^ 1;
-        o.imgA = (uint32_t)(s ? hi : lo) * 16u;
-        o.imgB = (uint32_t)(s ? lo : hi) * 16u;
+        o.imgA = (uint32_t)rswz_f4(f + s) * 16u;
+        o.imgB = (uint32_t)rswz_f4(f + 1 - s) * 16u;
     }
     if (!rev) {
         o.rowA = (uint32_t)(f + s) * 16u;
@@ -154,17 +170,16 @@ __device__ __forceinline__ void transpose_image(const float* __restrict__ bN, fl
             }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const float col[4] = {r[0][c], r[1][c], r[2][c], r[3][c]};
-                sts_vec<4>(bT, (w0 + c) * H + h0, col);
+                *reinterpret_cast<float4*>(bT + rswz_pos((w0 + c) * H + h0)) = make_float4(r[0][c], r[1][c], r[2][c], r[3][c]);
             }
         }
     } else {
         for (int q = tid; q < L; q += nthreads) {
             const int w = q / H, h = q - w * H;
-            bT[swz_pos(q)] = bN[h * W + w];
+            bT[rswz_pos(q)] = bN[h * W + w];
         }
     }
-    for (int p = L + tid; p < Lb; p += nthreads) bT[swz_pos(p)] = 0.0f;
+    for (int p = L + tid; p < Lb; p += nthreads) bT[rswz_pos(p)] = 0.0f;
 }
 
 // ---- out[p] = aN[p] + aT[w*H + h]: aN linear, aT swizzled ----------------------------------------------------------
@@ -178,7 +193,10 @@ __device__ __forceinline__ void merge_out_linear(TO* __restrict__ out, const flo
             const int h0 = bh << 2, w0 = bw << 2;
             float col[4][4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) lds_vec<4>(aT, (w0 + c) * H + h0, col[c]);
+            for (int c = 0; c < 4; ++c) {
+                const float4 t = *reinterpret_cast<const float4*>(aT + rswz_pos((w0 + c) * H + h0));
+                col[c][0] = t.x; col[c][1] = t.y; col[c][2] = t.z; col[c][3] = t.w;
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float4 t = *reinterpret_cast<const float4*>(aN + (h0 + i) * W + w0);
@@ -189,7 +207,7 @@ __device__ __forceinline__ void merge_out_linear(TO* __restrict__ out, const flo
     } else {
         for (int pp = tid; pp < L; pp += nthreads) {
             const int h = pp / W, w = pp - h * W;
-            out[pp] = Elem<TO>::from_f(aN[pp] + aT[swz_pos(w * H + h)]);
+            out[pp] = Elem<TO>::from_f(aN[pp] + aT[rswz_pos(w * H + h)]);
         }
     }
 }
@@ -207,8 +225,9 @@ __device__ __forceinline__ float max8(const f2 (&v)[4]) {
 constexpr float kEMin = 0.015625f;
 constexpr float kEMax = 268435456.0f;
 
-inline size_t ring_fwd_smem(int64_t L, int slots) {
-    return sizeof(float) * (size_t)(4 * buf_len(L)) + (size_t)(4 * slots * kRows * kChunkBytesF32) + 8 * (size_t)(1 + 4 * slots);
+inline size_t ring_fwd_smem(int64_t L, int warps, int slots) {      // images + ring + mbarriers (image, ring, carry) + carry values
+    return sizeof(float) * (size_t)(4 * buf_len(L)) + (size_t)(4 * warps * slots * kRows * kChunkBytesF32) +
+           8 * (size_t)(1 + 4 * warps * slots + 8) + 8 * sizeof(float);
 }
 inline size_t ring_bwd_smem(int64_t L, int slots) {
     return sizeof(float) * (size_t)(6 * buf_len(L)) + (size_t)(4 * slots * kRows * kChunkBytesF32) + 8 * (size_t)(2 + 4 * slots);
