@@ -462,6 +462,92 @@ def test_ss2d_unfused_fallback_large_L(xf):
         assert rel_err(n(leaves[k].grad), gr) < TOL32, f"d{k}"
 
 
+def test_ss2d_scan_4d_delta_and_no_grad(xf):
+    """delta given as (B, 4, D, L) gets its gradient back in that shape; under torch.no_grad() nothing is recorded even though
+    the parameters require grad"""
+    rng = np.random.default_rng(3)
+    Bsz, D, N, H, W = 2, 3, 1, 20, 16
+    c = _rand_ss2d(rng, Bsz, D, N, H, W)
+    lv = {k: t(c[k]).requires_grad_(True) for k in SS2D_KEYS}
+    d4 = lv["delta"].detach().view(Bsz, 4, D, H * W).clone().requires_grad_(True)
+    y = xf.ss2d_scan(lv["x"], d4, lv["A"], lv["Bs"], lv["Cs"], lv["Ds"], lv["delta_bias"])
+    y.backward(t(c["dy"]))
+    assert d4.grad.shape == d4.shape
+    grads = oracle.ss2d_bwd(c["x"], c["delta"], c["A"], c["Bs"], c["Cs"], c["Ds"], c["delta_bias"], c["dy"], True, "f64")
+    assert rel_err(n(d4.grad).reshape(Bsz, 4 * D, -1), grads[1]) < TOL32
+    with torch.no_grad():
+        y2 = xf.ss2d_scan(lv["x"], lv["delta"], lv["A"], lv["Bs"], lv["Cs"], lv["Ds"], lv["delta_bias"])
+        ys = xf.selective_scan_fn(xf.cross_scan_fn(lv["x"]).view(Bsz, -1, H * W), lv["delta"], lv["A"], lv["Bs"], lv["Cs"], lv["Ds"],
+                                  lv["delta_bias"], True, True)
+    assert y2.grad_fn is None and not y2.requires_grad and ys.grad_fn is None
+    assert rel_err(n(y2), n(y)) < 1e-6
+
+
+# ================================================================================================ fusion cores
+def _core_module(g, prefix, device):
+    """stands in for the reference module object: exactly the attributes the fused cores read (models/fusion_vmamba.py
+    :470-478, :801-808), filled with the parameters the reference recorded in tests/golden/cores.npz"""
+    import types
+    D = g[prefix + "out_norm.weight"].shape[0]
+    norm = torch.nn.LayerNorm(D).to(device)
+    with torch.no_grad():
+        norm.weight.copy_(torch.from_numpy(g[prefix + "out_norm.weight"]))
+        norm.bias.copy_(torch.from_numpy(g[prefix + "out_norm.bias"]))
+    mod = types.SimpleNamespace(out_norm=norm, channel_first=bool(int(g[prefix + "channel_first"])), x_proj_bias=None)
+    for k in ("x_proj_weight", "dt_projs_weight", "dt_projs_bias", "A_logs", "Ds"):
+        setattr(mod, k, torch.from_numpy(g[prefix + k]).to(device).requires_grad_(True))
+    return mod
+
+
+def _check_core_grads(g, prefix, mod, inputs, tol):
+    for name, leaf in inputs.items():
+        assert rel_err(n(leaf.grad), g[prefix + "d" + name]) < tol, "d" + name
+    for k in ("x_proj_weight", "dt_projs_weight", "dt_projs_bias", "A_logs", "Ds"):
+        assert rel_err(n(getattr(mod, k).grad), g[prefix + "grad_" + k]) < tol, k
+    assert rel_err(n(mod.out_norm.weight.grad), g[prefix + "grad_out_norm.weight"]) < tol
+    assert rel_err(n(mod.out_norm.bias.grad), g[prefix + "grad_out_norm.bias"]) < tol
+
+
+@pytest.mark.parametrize("via_patch", [False, True])
+def test_shallow_fusion_core_golden(xf, golden, via_patch):
+    """ShallowFuse_SS2Dv4.forward_corev2 (models/fusion_vmamba.py:777-845) as the reference recorded it: both outputs, the
+    gradients of both inputs and of every parameter -- through model.shallow_fuse_core and through the function
+    patch.install(fused=True) puts in the reference class."""
+    import xfmamba_b200.patch as xfpatch
+    from xfmamba_b200 import model as M
+    g = golden("cores")
+    mod = _core_module(g, "shallow_", dev())
+    x, x2 = t(g["shallow_x"]).requires_grad_(True), t(g["shallow_x2"]).requires_grad_(True)
+    if via_patch:
+        y, y2 = xfpatch._fused_shallow_core(mod, x, x2, force_fp32=False, no_einsum=True)
+    else:
+        ys = M.shallow_fuse_core(x, x2, mod.x_proj_weight, mod.dt_projs_weight, mod.dt_projs_bias, mod.A_logs, mod.Ds)
+        y, y2 = (xfpatch._finish(mod, v, x) for v in ys)
+    assert rel_err(n(y), g["shallow_y"]) < TOL32 and rel_err(n(y2), g["shallow_y2"]) < TOL32
+    ((y * t(g["shallow_gy"])).sum() + (y2 * t(g["shallow_gy2"])).sum()).backward()
+    _check_core_grads(g, "shallow_", mod, dict(x=x, x2=x2), 2e-4)
+
+
+@pytest.mark.parametrize("via_patch", [False, True])
+def test_deep_fusion_core_golden(xf, golden, via_patch):
+    """Cross_SS2Dv5.forward_corev2 (models/fusion_vmamba.py:446-578): three streams, one parameter set, the view streams
+    reading Cs of the fused stream (:536-538, 567-569) -- outputs, input gradients and every parameter gradient."""
+    import xfmamba_b200.patch as xfpatch
+    from xfmamba_b200 import model as M
+    g = golden("cores")
+    mod = _core_module(g, "deep_", dev())
+    x, x2, xfu = (t(g["deep_" + k]).requires_grad_(True) for k in ("x", "x2", "xf"))
+    if via_patch:
+        y, y2, yf = xfpatch._fused_cross_core(mod, x, x2, xfu, force_fp32=False, no_einsum=True)
+    else:
+        ys = M.cross_fuse_core(x, x2, xfu, mod.x_proj_weight, mod.dt_projs_weight, mod.dt_projs_bias, mod.A_logs, mod.Ds)
+        y, y2, yf = (xfpatch._finish(mod, v, x) for v in ys)
+    for got, key in ((y, "deep_y"), (y2, "deep_y2"), (yf, "deep_yf")):
+        assert rel_err(n(got), g[key]) < TOL32, key
+    ((y * t(g["deep_gy"])).sum() + (y2 * t(g["deep_gy2"])).sum() + (yf * t(g["deep_gyf"])).sum()).backward()
+    _check_core_grads(g, "deep_", mod, dict(x=x, x2=x2, xf=xfu), 2e-4)
+
+
 def test_native_library_was_used(xf):
     """the driver checks which .so the test process loaded; make the launch counter prove it too"""
     from xfmamba_b200 import _lib

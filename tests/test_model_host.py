@@ -150,3 +150,66 @@ def test_config1_xfmamba_t_two_pairs_gpu_vs_cpu_oracle_path(monkeypatch):
     print(f"config 1 on the host (torch CPU dense layers + oracle scans): {time.perf_counter() - t0:.2f} s for 2 pairs")
     assert got.shape == (2, 2)
     assert rel_err(got.numpy(), want.numpy()) < 1e-4
+
+
+# ---- the fusion cores against the operator-level tensors the reference recorded (tests/golden/cores.npz), on CPU with the
+# oracle substituted for the CUDA operators: checks the host logic of model.shallow_fuse_core / cross_fuse_core and of the
+# functions patch.install(fused=True) puts in the reference classes (the GPU versions are in test_gpu_parity.py)
+def _core_module(g, prefix):
+    import types
+    D = g[prefix + "out_norm.weight"].shape[0]
+    norm = torch.nn.LayerNorm(D)
+    with torch.no_grad():
+        norm.weight.copy_(torch.from_numpy(g[prefix + "out_norm.weight"]))
+        norm.bias.copy_(torch.from_numpy(g[prefix + "out_norm.bias"]))
+    mod = types.SimpleNamespace(out_norm=norm, channel_first=bool(int(g[prefix + "channel_first"])), x_proj_bias=None)
+    for k in ("x_proj_weight", "dt_projs_weight", "dt_projs_bias", "A_logs", "Ds"):
+        setattr(mod, k, torch.from_numpy(g[prefix + k]))
+    return mod
+
+
+def _oracle_ops(monkeypatch):
+    import xfmamba_b200.model as M
+    for name in ("ss2d_scan", "cross_scan_fn", "selective_scan_fn", "swapping_scan", "swapping_merge", "layer_norm_2d", "dwconv3x3_silu", "dt_proj"):
+        monkeypatch.setattr(M.OPS, name, getattr(OracleOps, name))
+
+
+def test_shallow_fusion_core_golden_on_cpu(golden, monkeypatch):
+    import xfmamba_b200.patch as xfpatch
+    g = golden("cores")
+    _oracle_ops(monkeypatch)
+    mod = _core_module(g, "shallow_")
+    with torch.no_grad():
+        y, y2 = xfpatch._fused_shallow_core(mod, torch.from_numpy(g["shallow_x"]), torch.from_numpy(g["shallow_x2"]),
+                                            force_fp32=False, no_einsum=True)
+    assert rel_err(y.numpy(), g["shallow_y"]) < 1e-4 and rel_err(y2.numpy(), g["shallow_y2"]) < 1e-4
+
+
+def test_deep_fusion_core_golden_on_cpu(golden, monkeypatch):
+    import xfmamba_b200.patch as xfpatch
+    g = golden("cores")
+    _oracle_ops(monkeypatch)
+    mod = _core_module(g, "deep_")
+    with torch.no_grad():
+        ys = xfpatch._fused_cross_core(mod, torch.from_numpy(g["deep_x"]), torch.from_numpy(g["deep_x2"]),
+                                       torch.from_numpy(g["deep_xf"]), force_fp32=False, no_einsum=True)
+    for got, key in zip(ys, ("deep_y", "deep_y2", "deep_yf")):
+        assert rel_err(got.numpy(), g[key]) < 1e-4, key
+
+
+def test_fused_cores_keep_the_reference_for_other_modes():
+    """anything the fused kernels do not compute (unidi / bidi / cascade2d routes, an x_proj_bias, ssoflex=False) is NOT
+    rerouted: _reroutable says so, and the replacement then calls the saved reference method"""
+    import types
+    import xfmamba_b200.patch as xfpatch
+    plain = types.SimpleNamespace(x_proj_bias=None)
+    assert xfpatch._reroutable(plain, dict(force_fp32=False, no_einsum=True))
+    assert xfpatch._reroutable(plain, dict(scan_mode="cross2d", selective_scan_backend="oflex"))
+    for kw in (dict(scan_mode="unidi"), dict(scan_mode="bidi"), dict(scan_mode="cascade2d"), dict(scan_mode=3),
+               dict(ssoflex=False), dict(to_dt_softmax=True), dict(some_future_flag=1)):
+        assert not xfpatch._reroutable(plain, kw), kw
+    assert not xfpatch._reroutable(types.SimpleNamespace(x_proj_bias=torch.zeros(4)), {})
+    calls = []
+    mod = types.SimpleNamespace(x_proj_bias=None, _xfs_reference_corev2=lambda *a, **k: calls.append((a, k)) or "ref")
+    assert xfpatch._fused_cross_core(mod, 1, 2, 3, scan_mode="bidi") == "ref" and calls[0][1] == dict(scan_mode="bidi")
+    assert xfpatch._fused_shallow_core(mod, 1, 2, ssoflex=False) == "ref"

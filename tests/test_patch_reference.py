@@ -49,3 +49,29 @@ def test_fused_core_replacement_matches_reference_core(monkeypatch):
             monkeypatch.setattr(M.OPS, name, getattr(OracleOps, name))
         got = xfpatch._fused_ss2d_core(m, x)
     assert rel_err(got.numpy(), want.numpy()) < 1e-4
+
+
+def test_install_fused_only_reroutes_cross2d_and_uninstall_restores():
+    import functools
+    import xfmamba_b200.patch as xfpatch
+    ref = _refload.load()
+    fv = ref.fusion_vmamba
+    before = {n: getattr(fv, n) for n in xfpatch._NAMES}
+    init0, cross0, shallow0 = fv.SS2Dv2.__init__, fv.Cross_SS2Dv5.forward_corev2, fv.ShallowFuse_SS2Dv4.forward_corev2
+    try:
+        xfpatch.install(fv, fused=True)
+        xfpatch.install(fv, fused=True)                       # idempotent: the ORIGINALS stay saved
+        m = fv.SS2Dv2(d_model=8, d_state=1, forward_type="v05_noz", channel_first=True)
+        assert isinstance(m.forward_core, functools.partial) and m.forward_core.func.__func__ is xfpatch._fused_ss2d_core
+        assert m.forward_core.keywords == dict(force_fp32=False, no_einsum=True)
+        bidi = fv.SS2Dv2(d_model=8, d_state=1, forward_type="v052d_noz", channel_first=True)
+        assert bidi.forward_core.keywords["scan_mode"] == "bidi"
+        assert not xfpatch._reroutable(bidi, bidi.forward_core.keywords)      # stays on the reference core
+        assert fv.Cross_SS2Dv5.forward_corev2 is xfpatch._fused_cross_core
+        assert fv.Cross_SS2Dv5._xfs_reference_corev2 is cross0
+    finally:
+        xfpatch.uninstall(fv)
+    assert fv.SS2Dv2.__init__ is init0 and fv.Cross_SS2Dv5.forward_corev2 is cross0
+    assert fv.ShallowFuse_SS2Dv4.forward_corev2 is shallow0
+    assert all(getattr(fv, n) is v for n, v in before.items())
+    assert not hasattr(fv.Cross_SS2Dv5, "_xfs_reference_corev2")

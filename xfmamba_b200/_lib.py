@@ -142,3 +142,11 @@ def num_chunks(L: int) -> int:
 
 def launch_count() -> int:
     return int(lib().xfs_launch_count())
+
+
+def grad_needed(*tensors) -> bool:
+    """Evaluated by the operator wrappers BEFORE ``Function.apply``: inside ``forward`` grad mode is always off and
+    ``ctx.needs_input_grad`` only mirrors ``requires_grad`` of the inputs, which is True for parameters under ``torch.no_grad()``
+    as well -- inference would then write and keep the chunk states / statistics that only a backward pass reads."""
+    import torch
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors)

@@ -121,13 +121,13 @@ class SelectiveScanCuda(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda")
-    def forward(ctx, u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, oflex=True, backend=None):
+    def forward(ctx, u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, oflex=True, backend=None, need_grad=None):
         if backend not in _BACKENDS:
             raise RuntimeError(f"selective_scan: backend {backend!r} is not provided by xfmamba_b200 "
                                "(one sm_100a implementation; the torch path is test-only, see oracle/)")
         ctx.delta_softplus = delta_softplus
         ctx.b3, ctx.c3 = B.dim() == 3, C.dim() == 3
-        need = any(ctx.needs_input_grad)
+        need = any(ctx.needs_input_grad) if need_grad is None else bool(need_grad)     # see _lib.grad_needed
         out, states, saved = selective_scan_fwd_raw(u, delta, A, B, C, D, delta_bias, delta_softplus, oflex, need_states=need)
         if need:
             ctx.has_D, ctx.has_bias = D is not None, delta_bias is not None
@@ -150,7 +150,7 @@ class SelectiveScanCuda(torch.autograd.Function):
             dB = dB.squeeze(1)
         if ctx.c3:
             dC = dC.squeeze(1)
-        return du, ddelta, dA, dB, dC, dD, dbias, None, None, None
+        return du, ddelta, dA, dB, dC, dD, dbias, None, None, None, None
 
 
 def selective_scan_fn(
@@ -169,4 +169,5 @@ def selective_scan_fn(
     if backend == "torch":
         raise RuntimeError("selective_scan_fn(backend='torch'): the PyTorch path is not part of xfmamba_b200 "
                            "(no CPU fallback); use the reference's selective_scan_torch or oracle/ in tests")
-    return SelectiveScanCuda.apply(u, delta, A, B, C, D, delta_bias, delta_softplus, oflex, backend)
+    need = _lib.grad_needed(u, delta, A, B, C, D, delta_bias)
+    return SelectiveScanCuda.apply(u, delta, A, B, C, D, delta_bias, delta_softplus, oflex, backend, need)

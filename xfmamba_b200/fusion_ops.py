@@ -24,14 +24,6 @@ __all__ = ["SwappingScan_multiview", "SwappingMerge_multiview", "swapping_scan",
            "SS2DScanFn", "ss2d_fused_supported", "ss2d_fwd_raw", "ss2d_bwd_raw", "ss2d_acc_replicas"]
 
 
-def _swap_call(fn_name, a, b, outs, B, C, L, dev):
-    fn = getattr(_lib.lib(), fn_name)
-    with torch.cuda.device(dev):
-        rc = fn(_lib.ptr(a), _lib.ptr(b) if b is not None else _lib.ptr(outs[0]),
-                _lib.ptr(outs[0]) if b is not None else _lib.ptr(outs[1]), B, C, L, _lib.dtype_code(a), _lib.stream(dev))
-    _lib.check(rc, fn_name)
-
-
 def _swap_scan_raw(x, x2):
     dev = _lib.require_cuda(x, x2)
     if x.shape != x2.shape or x.dtype != x2.dtype:
@@ -199,7 +191,7 @@ class SS2DScanFn(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda")
-    def forward(ctx, x, delta, A, Bs, Cs, Ds, delta_bias, delta_softplus, oflex):
+    def forward(ctx, x, delta, A, Bs, Cs, Ds, delta_bias, delta_softplus, oflex, need_grad=None):
         if x.dim() != 4:
             raise RuntimeError(f"ss2d_scan: x must be (B, D, H, W); got {tuple(x.shape)}")
         Bsz, D, H, W = x.shape
@@ -211,7 +203,7 @@ class SS2DScanFn(torch.autograd.Function):
         _lib.require_cuda(x)
         if G != 4:
             raise RuntimeError(f"ss2d_scan: Bs/Cs must be (B, 4, N, L); got {tuple(Bs.shape)}")
-        need = any(ctx.needs_input_grad)
+        need = any(ctx.needs_input_grad) if need_grad is None else bool(need_grad)     # see _lib.grad_needed
         fused = ss2d_fused_supported(D, N, H, W, x.dtype, False) and (not need or ss2d_fused_supported(D, N, H, W, x.dtype, True))
         x, delta, A, Bs, Cs = (t.contiguous() for t in (x, delta, A, Bs, Cs))
         Ds = None if Ds is None else Ds.contiguous()
@@ -254,7 +246,7 @@ class SS2DScanFn(torch.autograd.Function):
             du, ddelta, dA, dBs, dCs, dDs, dbias = selective_scan_bwd_raw(xs, delta, A, Bs, Cs, Ds, delta_bias, dys, states,
                                                                           ctx.delta_softplus)
             dx = cross_merge_raw(du.view(Bsz, 4, D, L), H, W).view(Bsz, D, H, W)
-        return dx, ddelta, dA, dBs, dCs, dDs, dbias, None, None
+        return dx, ddelta, dA, dBs, dCs, dDs, dbias, None, None, None
 
 
 def ss2d_scan(x, delta, A, Bs, Cs, Ds=None, delta_bias=None, delta_softplus=True, oflex=True):
@@ -265,4 +257,7 @@ def ss2d_scan(x, delta, A, Bs, Cs, Ds=None, delta_bias=None, delta_softplus=True
     order: f32 when ``oflex`` else x.dtype -- exactly ``cross_merge_fn(selective_scan_fn(cross_scan_fn(x).view(B,-1,L),
     delta, A, Bs, Cs, Ds, delta_bias, delta_softplus, oflex).view(B,4,-1,H,W))``.
     """
-    return SS2DScanFn.apply(x, delta, A, Bs, Cs, Ds, delta_bias, delta_softplus, oflex)
+    if x.dim() == 4 and delta.dim() == 4:          # (B, 4, D, L): flatten OUTSIDE the Function so that autograd un-flattens ddelta
+        delta = delta.reshape(x.shape[0], 4 * x.shape[1], -1)
+    need = _lib.grad_needed(x, delta, A, Bs, Cs, Ds, delta_bias)
+    return SS2DScanFn.apply(x, delta, A, Bs, Cs, Ds, delta_bias, delta_softplus, oflex, need)

@@ -13,7 +13,7 @@ __all__ = ["layer_norm_2d", "LayerNorm2dFn"]
 class LayerNorm2dFn(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda")
-    def forward(ctx, x, weight, bias, eps):
+    def forward(ctx, x, weight, bias, eps, need_grad=None):
         dev = _lib.require_cuda(x, weight, bias)
         if x.dim() < 3:
             raise RuntimeError(f"layer_norm_2d expects (B, C, ...) with at least one spatial dim; got {tuple(x.shape)}")
@@ -23,7 +23,7 @@ class LayerNorm2dFn(torch.autograd.Function):
         w = None if weight is None else weight.float().contiguous()
         b = None if bias is None else bias.float().contiguous()
         y = torch.empty_like(x)
-        need = any(ctx.needs_input_grad)
+        need = any(ctx.needs_input_grad) if need_grad is None else bool(need_grad)     # see _lib.grad_needed
         mean = torch.empty((B, HW), dtype=torch.float32, device=dev) if need else None
         rstd = torch.empty((B, HW), dtype=torch.float32, device=dev) if need else None
         if x.numel():
@@ -57,8 +57,8 @@ class LayerNorm2dFn(torch.autograd.Function):
             dw = dw.to(ctx.wdtype)
         if db is not None and ctx.wdtype is not None:
             db = db.to(ctx.wdtype)
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
 def layer_norm_2d(x, weight=None, bias=None, eps=1e-5):
-    return LayerNorm2dFn.apply(x, weight, bias, eps)
+    return LayerNorm2dFn.apply(x, weight, bias, eps, _lib.grad_needed(x, weight, bias))
