@@ -7,6 +7,11 @@ fused forward kernel + one fused backward kernel over that batch (plus the zero-
 GPUs every rank runs the same per-GPU batch (weak scaling, batch sharded) and the parameter gradients
 (dA, dDs, ddelta_bias) are all-reduced with NCCL each step -- the only exchange the path has.
 
+The timed region repeats the K-step block until it is at least one second long (`inner_repeats` in the JSON line;
+ms_per_step is per step), so that clocks are sampled a few hundred times.  After the micro-benchmark every rank also runs
+BASELINE config 4 -- an XFMamba-B training step (32 pairs per GPU, DDP + NCCL all-reduce of the 104 M-parameter gradient) --
+and reports it as `model_train` (pairs/s, ms per step, exposed all-reduce time); `--no-model` skips that leg.
+
 The JSON line carries: value (pairs/s, inputs resident in HBM), e2e (same step through the public autograd API with
 pinned HOST buffers: H2D of every input + D2H of a scalar each step), roofline of the dominant kernel (fused backward)
 and of the forward (CUDA-event time of each launch inside the timed region vs MEASURED_PEAKS.json), cpu_baseline (the
@@ -29,6 +34,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(name="ss2d_stage1_fwd_bwd", H=56, W=56, D=192, N=1, K=4)
+FWD_KERNEL = "ss2d_ring_fwd_kernel"     # what xfs_ss2d_fwd / xfs_ss2d_bwd launch for this workload in fp32 (profiles/traffic.json keys)
+BWD_KERNEL = "ss2d_bwd_kernel"
 FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
@@ -113,6 +120,13 @@ def synth_inputs_np(batch, seed=0):
                 dy=f(batch, w["D"], L))
 
 
+def cpu_threads():
+    """all host cores for the oracle's OpenMP loops -- set explicitly: torch.distributed.run exports OMP_NUM_THREADS=1"""
+    import oracle
+    cores = os.cpu_count() or 1
+    return oracle.set_threads(cores)
+
+
 def cpu_baseline(sample_batch, reps=1):
     """fwd+bwd of the same path with the CPU oracle (C, OpenMP) on `sample_batch` images; returns pairs/s"""
     import oracle
@@ -132,9 +146,14 @@ def run_reference(args):
     """reference arm: CPU restatement (oracle port) on the host cores; rank 0 only"""
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    sample = 4                                   # images per step (2 two-view pairs), same shape as the GPU workload
+    cores = cpu_threads()
+    # images per step: the GPU arm's batch when the K-step run then fits ~2.5 minutes on this box, else the largest
+    # power-of-two sample that does (the metric is pairs/s, i.e. normalised by the batch; `same_batch` says which)
+    _, secs4 = cpu_baseline(4)
+    per_image = secs4 / 4
+    sample = args.batch
+    while sample > 4 and per_image * sample * (args.steps + 1) > 150.0:
+        sample //= 2
     for _ in range(min(args.warmup, 1)):
         cpu_baseline(sample)
     t0 = time.perf_counter()
@@ -147,9 +166,11 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": w["name"], "H": w["H"], "W": w["W"], "d_inner": w["D"], "d_state": w["N"], "K": w["K"],
-                       "images_per_step": sample},
+                       "images_per_step": sample, "images_per_gpu": args.batch, "same_batch": sample == args.batch,
+                       "note": "CPU arm = oracle/ (a C + OpenMP restatement of the reference's torch path), not the "
+                               "reference's Python loop, which is ~20x slower (0.65 s per (2, 768, 3136) forward scan)"},
             "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port",
-                             "sample": f"{sample} images (2 pairs) per step, SS2D core fwd+bwd, oracle/ C port with OpenMP"},
+                             "sample": f"{sample} images ({sample // 2} pairs) per step, SS2D core fwd+bwd, oracle/ C port with OpenMP on {cores} threads"},
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -187,12 +208,13 @@ def run_ours(args):
     # dBs / dCs accumulators: replicated (see xfs_ss2d_bwd_args.acc_replicas), summed over the replicas inside ss2d_bwd_raw
     n_rep = fusion_ops.ss2d_acc_replicas(w["D"], L, batch)
     acc_shape = tuple(d["Bs"].shape) if n_rep == 1 else (n_rep,) + tuple(d["Bs"].shape)
-    grads = (torch.empty_like(d["x"]), torch.empty_like(d["delta"]), torch.empty_like(d["A"]),
-             torch.empty(acc_shape, dtype=torch.float32, device=dev), torch.empty(acc_shape, dtype=torch.float32, device=dev),
-             torch.empty_like(d["Ds"]), torch.empty_like(d["delta_bias"]))
-    # dA, dDs, ddelta_bias are the parameter gradients.  Two buckets alternate so that the all-reduce of step i (NCCL's own
-    # stream) overlaps the kernels of step i+1, as a gradient bucket does with the rest of a backward pass.
-    buckets = [FlatBucket([grads[2], grads[5], grads[6]]) for _ in range(2)]
+    # dA, dDs, ddelta_bias are the parameter gradients: the backward kernel accumulates them DIRECTLY into the views of a
+    # flat bucket (one memset, no pack copies, one all-reduce).  Two buckets alternate so that the all-reduce of step i
+    # (NCCL's own stream) overlaps the kernels of step i+1, as a gradient bucket does with the rest of a backward pass.
+    buckets = [FlatBucket([d["A"], d["Ds"], d["delta_bias"]]) for _ in range(2)]
+    shared = (torch.empty_like(d["x"]), torch.empty_like(d["delta"]),
+              torch.empty(acc_shape, dtype=torch.float32, device=dev), torch.empty(acc_shape, dtype=torch.float32, device=dev))
+    grad_sets = [(shared[0], shared[1], bk.views[0], shared[2], shared[3], bk.views[1], bk.views[2]) for bk in buckets]
     pending = [None, None]
     step_no = [0]
 
@@ -206,9 +228,16 @@ def run_ours(args):
         fusion_ops.ss2d_fwd_raw(*[d[k] for k in keys], True, torch.float32, True, y, states)
         if timed:
             e1.record()
+        i = step_no[0] & 1
+        step_no[0] += 1
+        if pending[i] is not None:
+            pending[i].wait()                          # the bucket's previous reduction (two steps ago) must be done
+            pending[i] = None
+        grads = grad_sets[i]
         # zero-fills of the accumulated gradients are part of the step but not of the kernel's event bracket
-        for acc in (grads[2], grads[3], grads[4], grads[5], grads[6]):
-            acc.zero_()
+        buckets[i].flat.zero_()
+        grads[3].zero_()
+        grads[4].zero_()
         if timed:
             e1b.record()
         out = fusion_ops.ss2d_bwd_raw(*[d[k] for k in keys], d["dy"], states, True, grads, zero=False, reduce=False)
@@ -219,11 +248,6 @@ def run_ours(args):
         if out[3].dim() == 5:          # sum of the accumulator replicas: part of the step, outside the kernel's event bracket
             out[3].sum(0), out[4].sum(0)
         if world > 1:   # data-parallel exchange of the parameter gradients (training step): one NCCL all-reduce
-            i = step_no[0] & 1
-            step_no[0] += 1
-            if pending[i] is not None:
-                pending[i].wait()                      # the bucket's previous reduction (two steps ago) must be done
-            buckets[i].pack([grads[2], grads[5], grads[6]])
             pending[i] = dist.all_reduce(buckets[i].flat, async_op=True)
 
     def sync_all():
@@ -238,12 +262,26 @@ def run_ours(args):
     for _ in range(args.warmup):
         step(False)
     sync_all()
+    # the K-step block is repeated until the timed region is >= 1 s (every step is timed; ms_per_step is per step)
+    c0, c1 = ev(), ev()
+    c0.record()
+    for _ in range(3):
+        step(False)
+    c1.record()
+    sync_all()
+    est_ms = c0.elapsed_time(c1) / 3
+    repeats = max(1, min(500, int(1000.0 / max(est_ms * args.steps, 1e-3)) + 1))
+    if world > 1:
+        rt = torch.tensor([repeats], device=dev)
+        dist.all_reduce(rt, op=dist.ReduceOp.MAX)
+        repeats = int(rt.item())
+    n_steps = args.steps * repeats
     sampler = ClockSampler(local)
     sampler.start()
     before = _lib.launch_count()
     t_start, t_end = ev(), ev()
     t_start.record()
-    for _ in range(args.steps):
+    for _ in range(n_steps):
         step(True)
     for i in range(2):                                  # the last reductions belong to the timed steps
         if pending[i] is not None:
@@ -317,7 +355,7 @@ def run_ours(args):
         e2e_ms = float(tt.item())
 
     pairs_per_step = world * batch / 2
-    value = pairs_per_step * args.steps / (elapsed_ms / 1e3)
+    value = pairs_per_step * n_steps / (elapsed_ms / 1e3)
     e2e_value = pairs_per_step * args.steps / (e2e_ms / 1e3)
     fb, bb = alg_bytes(batch, w["D"], w["N"], L, s)
     peak, peak_src = peaks()
@@ -327,7 +365,8 @@ def run_ours(args):
                                      "frac_of_8TBs": nbytes / (ms * 1e-3) / 8e12}
     line = {
         "metric": "two_view_pairs_per_sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": elapsed_ms / n_steps, "inner_repeats": repeats, "timed_region_s": elapsed_ms / 1e3,
+        "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": {"workload": w["name"], "H": w["H"], "W": w["W"], "d_inner": w["D"], "d_state": w["N"], "K": w["K"],
                    "images_per_gpu": batch, "pairs_per_step": pairs_per_step, "parallelism": f"dp{world}",
@@ -336,13 +375,21 @@ def run_ours(args):
                 "ms_per_step": e2e_ms / args.steps, "note": "pinned host inputs, double-buffered H2D on a copy stream"},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": roof(bb, bwd_ms, "ss2d_bwd_kernel"),
-        "roofline_fwd": roof(fb, fwd_ms, "ss2d_fwd_kernel"),
+        "roofline": roof(bb, bwd_ms, BWD_KERNEL),
+        "roofline_fwd": roof(fb, fwd_ms, FWD_KERNEL if args.dtype == "f32" else "ss2d_fwd_kernel"),
     }
+    if not args.no_model:
+        # BASELINE config 4 (north_star's end-to-end number) under the same launch: XFMamba-B training step, DDP + NCCL
+        import bench_model
+        del d, y, states, shared, grad_sets, buckets, bufs, pin
+        torch.cuda.empty_cache()
+        try:
+            line["model_train"] = bench_model.train_leg("xfmamba_b_train", args.model_batch, args.model_steps, 3, dev, world, rank, local)
+        except Exception as e:                      # never lose the micro-benchmark line over the model leg
+            line["model_train"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank == 0:
         if world == 1 and not args.no_cpu:
-            cores = os.cpu_count() or 1
-            os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+            cores = cpu_threads()
             sample = 8
             v, secs = cpu_baseline(sample, reps=2)
             line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": "port",
@@ -364,6 +411,9 @@ def main():
     ap.add_argument("--workload", default="ss2d", help="ss2d (default, BASELINE config 2) or xfmamba_{t,s,b}_infer / "
                     "xfmamba_{s,b}_train / xfmamba_b_hires (end-to-end model, configs 3-5; see bench_model.py)")
     ap.add_argument("--no-graph", action="store_true", help="model inference workloads: eager instead of a CUDA graph")
+    ap.add_argument("--no-model", action="store_true", help="skip the model_train leg (XFMamba-B training step, config 4)")
+    ap.add_argument("--model-batch", type=int, default=32, help="pairs per GPU of the model_train leg")
+    ap.add_argument("--model-steps", type=int, default=8, help="timed steps of the model_train leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -25,6 +25,78 @@ WORKLOADS = {
 }
 
 
+def train_leg(workload, batch, steps, warmup, dev, world, rank, local, amp=False):
+    """BASELINE config 4 as a leg of the default bench.py run: XFMamba-B training step (fwd + bwd + gradient all-reduce +
+    Adam) on `batch` synthetic two-view pairs per GPU; the process group (if any) is already initialised.  Returns the
+    `model_train` object of the JSON line.  `allreduce_exposed_ms` = step time with DDP's bucketed NCCL all-reduce minus the
+    step time of the same model under `no_sync()` (no collective at all), max over ranks."""
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from xfmamba_b200 import _lib
+    from xfmamba_b200.model import TwoViewXFMamba
+
+    w = WORKLOADS[workload]
+    torch.manual_seed(0)
+    model = TwoViewXFMamba(outputs=w["outputs"], type=w["type"]).to(dev)
+    nparam = sum(p.numel() for p in model.parameters())
+    gen = torch.Generator(device="cpu").manual_seed(rank)
+    img = w["img"]
+    xa = torch.randn(batch, 1, img, img, generator=gen).to(dev)
+    xb = torch.randn(batch, 1, img, img, generator=gen).to(dev)
+    yt = torch.randint(0, w["outputs"], (batch,), generator=gen).to(dev)
+    model.train()
+    ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True) if world > 1 else model
+    opt = torch.optim.Adam(ddp.parameters(), lr=1e-4, weight_decay=1e-5)          # reference 1_train_model.py:135-141
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            loss = F.cross_entropy(ddp(xa, xb).float(), yt)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def timed(n, nosync=False):
+        import contextlib
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        before = _lib.launch_count()
+        e0.record()
+        with (ddp.no_sync() if (nosync and world > 1) else contextlib.nullcontext()):
+            for _ in range(n):
+                step()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, (_lib.launch_count() - before) // n
+
+    for _ in range(warmup):
+        step()
+    ms, launches = timed(steps)
+    out = {"workload": workload, "model": f"XFMamba-{w['type']}", "params_m": round(nparam / 1e6, 2), "pairs_per_gpu": batch,
+           "global_pairs": batch * world, "steps": steps, "ms_per_step": ms, "pairs_per_s": batch * world / (ms / 1e3),
+           "grad_bytes_allreduced": nparam * 4 if world > 1 else 0, "xfscan_launches_per_step": launches,
+           "dtype": "bf16 autocast" if amp else "f32", "mode": "fwd + bwd + DDP/NCCL gradient all-reduce + Adam"}
+    if world > 1:
+        ms_ns, _ = timed(max(3, steps // 2), nosync=True)
+        out["ms_per_step_no_allreduce"] = ms_ns
+        out["allreduce_exposed_ms"] = max(0.0, ms - ms_ns)
+    else:
+        out["allreduce_exposed_ms"] = 0.0
+    del ddp, model, opt, xa, xb, yt
+    torch.cuda.empty_cache()
+    return out
+
+
 def run(args, ClockSampler):
     import torch
     import torch.distributed as dist

@@ -14,7 +14,7 @@ from pathlib import Path
 import numpy as np
 
 __all__ = [
-    "build", "lib", "route_table", "cross_scan", "cross_merge", "cross_merge_1b1", "swap_scan", "swap_merge",
+    "build", "lib", "set_threads", "route_table", "cross_scan", "cross_merge", "cross_merge_1b1", "swap_scan", "swap_merge",
     "selective_scan_fwd", "selective_scan_bwd", "ss2d_fwd", "ss2d_bwd", "bf16_round", "np_cross_scan", "layernorm2d",
     "dwconv3x3_silu", "dwconv3x3_silu_bwd", "dt_proj", "dt_proj_bwd",
 ]
@@ -40,6 +40,14 @@ def lib() -> ctypes.CDLL:
         _lib.xfo_route_index.restype = ctypes.c_int64
         _lib.xfo_route_index.argtypes = [ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int]
     return _lib
+
+
+def set_threads(n: int = 0) -> int:
+    """OpenMP threads of the oracle's loops (0: leave as is); returns the count in effect (1 without OpenMP)."""
+    L = lib()
+    L.xfo_set_threads.restype = ctypes.c_int
+    L.xfo_set_threads.argtypes = [ctypes.c_int]
+    return int(L.xfo_set_threads(int(n)))
 
 
 def _p(a):

@@ -43,6 +43,15 @@ typedef XFO_REAL real_t;
  * models/csm_triton.py:25-35
  * ------------------------------------------------------------------------------------------- */
 #ifdef XFO_BUILD_ROUTES
+/* thread count of the OpenMP loops (bench.py's CPU baseline): a launcher may have exported OMP_NUM_THREADS=1
+ * (torch.distributed.run does) long before this library is loaded, so the count is set explicitly */
+#ifdef _OPENMP
+#include <omp.h>
+int xfo_set_threads(int n) { if (n > 0) omp_set_num_threads(n); return omp_get_max_threads(); }
+#else
+int xfo_set_threads(int n) { (void)n; return 1; }
+#endif
+
 /* spatial offset (h*W+w) that scan position l of direction k reads */
 static inline int64_t xfo_route(int k, int64_t l, int64_t H, int64_t W, int scans) {
     int64_t L = H * W;
