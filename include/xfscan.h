@@ -198,6 +198,109 @@ XFS_API int xfs_ss2d_fwd(const xfs_ss2d_fwd_args* a, xfs_stream_t stream);
 XFS_API int xfs_ss2d_bwd(const xfs_ss2d_bwd_args* a, xfs_stream_t stream);
 
 /* -------------------------------------------------------------------------------------------------------------
+ * Deep fusion: the three SS2D streams of Cross_SS2Dv5.forward_corev2 (models/fusion_vmamba.py:446-578) in ONE launch.
+ * Stream order is free; the reference runs x_fuse, x, x2 (:483-512, :517-543, :548-574).  All streams share A, Ds,
+ * delta_bias (one parameter set, :470-478); every stream has its own x, delta, Bs; Cs[s] may alias -- the two view
+ * streams read the fused stream's C (:536-538, :567-569), so callers pass the same pointer three times.  Shapes per
+ * stream as xfs_ss2d_fwd / xfs_ss2d_bwd; H*W <= 64 and N <= 16 (the fusion blocks run on the last backbone stage: 7x7
+ * tokens, N = 16); other shapes return XFS_ERR_UNSUPPORTED and callers use xfs_ss2d_fwd per stream.
+ * bwd: dBs[s] / dCs[s] (batch, 4, N, L) f32 are ACCUMULATED into (zero-filled by the caller; aliased dCs sum the
+ * three streams); dA, dDs, ddelta_bias accumulate over the streams as they do over the batch.
+ * ----------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    const void* x[3];
+    const void* delta[3];
+    const void* Bs[3];
+    const void* Cs[3];
+    void* y[3];
+    float* states[3];        /* each nullable */
+    const float* A;
+    const float* Ds;         /* nullable */
+    const float* delta_bias; /* nullable */
+    int64_t batch, D, N, H, W;
+    int32_t dtype, out_dtype, delta_softplus, nstreams;   /* nstreams in 1..3 */
+} xfs_cross_ss2d_x3_fwd_args;
+
+typedef struct {
+    const void* x[3];
+    const void* delta[3];
+    const void* Bs[3];
+    const void* Cs[3];
+    const void* dy[3];
+    void* dx[3];
+    void* ddelta[3];
+    float* dBs[3];
+    float* dCs[3];
+    const float* A;
+    const float* Ds;
+    const float* delta_bias;
+    float* dA;
+    float* dDs;
+    float* ddelta_bias;
+    int64_t batch, D, N, H, W;
+    int32_t dtype, dout_dtype, delta_softplus, nstreams;
+} xfs_cross_ss2d_x3_bwd_args;
+
+XFS_API int xfs_cross_ss2d_x3_supported(int64_t N, int64_t H, int64_t W);
+XFS_API int xfs_cross_ss2d_x3_fwd(const xfs_cross_ss2d_x3_fwd_args* a, xfs_stream_t stream);
+XFS_API int xfs_cross_ss2d_x3_bwd(const xfs_cross_ss2d_x3_bwd_args* a, xfs_stream_t stream);
+
+/* -------------------------------------------------------------------------------------------------------------
+ * Shallow fusion: SwappingScan_multiview + selective scan (K = 2 halves) + SwappingMerge_multiview of
+ * ShallowFuse_SS2Dv4.forward_corev2 (models/fusion_vmamba.py:812, 831-835; :189-241) in ONE kernel: the scan input
+ * of half k, channel c is x2[b, c] when (c even) == (k == 0), else x[b, c] (:198-214); output half 0 -> y, half 1 -> y2.
+ *   x, x2 : (batch, D, L) dtype            delta : (batch, 2*D, L) dtype           A : (2*D, N) f32
+ *   Bs, Cs: (batch, 2, N, L) dtype         Ds, delta_bias : (2*D) f32 or NULL      y, y2 : (batch, D, L) out_dtype
+ *   states: (batch, 2*D, 1, N) f32, nullable.    L <= 64, N <= 16 (else XFS_ERR_UNSUPPORTED: compose
+ *   xfs_swap_scan + xfs_selective_scan_fwd + xfs_swap_merge).
+ * bwd follows the reference AS WRITTEN: dy / dy2 are the gradients of halves 0 / 1 (SwappingMerge.backward stacks them,
+ * :234-241) and the scan-input gradient of half 0 goes to dx, of half 1 to dx2 WITHOUT un-swapping the even channels
+ * (SwappingScan.backward, :217-221).  dA, dBs, dCs, dDs, ddelta_bias are accumulated into (caller zero-fills).
+ * ----------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    const void* x;
+    const void* x2;
+    const void* delta;
+    const float* A;
+    const void* Bs;
+    const void* Cs;
+    const float* Ds;         /* nullable */
+    const float* delta_bias; /* nullable */
+    void* y;
+    void* y2;
+    float* states;           /* nullable */
+    int64_t batch, D, N, L;
+    int32_t dtype, out_dtype, delta_softplus, reserved;
+} xfs_swap_scan_fused_fwd_args;
+
+typedef struct {
+    const void* x;
+    const void* x2;
+    const void* delta;
+    const float* A;
+    const void* Bs;
+    const void* Cs;
+    const float* Ds;
+    const float* delta_bias;
+    const void* dy;
+    const void* dy2;
+    void* dx;
+    void* dx2;
+    void* ddelta;
+    float* dA;
+    float* dBs;
+    float* dCs;
+    float* dDs;
+    float* ddelta_bias;
+    int64_t batch, D, N, L;
+    int32_t dtype, dout_dtype, delta_softplus, reserved;
+} xfs_swap_scan_fused_bwd_args;
+
+XFS_API int xfs_swap_scan_fused_supported(int64_t N, int64_t L);
+XFS_API int xfs_swap_scan_fused_fwd(const xfs_swap_scan_fused_fwd_args* a, xfs_stream_t stream);
+XFS_API int xfs_swap_scan_fused_bwd(const xfs_swap_scan_fused_bwd_args* a, xfs_stream_t stream);
+
+/* -------------------------------------------------------------------------------------------------------------
  * LayerNorm2d: LayerNorm over the channel dimension of a channel-first tensor, the consumer of the merged scan output
  * (reference LayerNorm2d, models/fusion_vmamba.py:52-57; out_norm at :1183-1188).  x, y, dy, dx: (B, C, HW) dtype;
  * weight, bias: (C) f32 or NULL; mean, rstd: (B, HW) f32 (written by fwd when non-NULL, required by bwd);

@@ -550,6 +550,64 @@ def test_deep_fusion_core_golden(xf, golden, via_patch):
     _check_core_grads(g, "deep_", mod, dict(x=x, x2=x2, xf=xfu), 2e-4)
 
 
+@pytest.mark.parametrize("shape", [(2, 5, 16, 7, 7), (1, 8, 4, 5, 6), (2, 3, 1, 8, 8), (1, 33, 16, 7, 7)])
+def test_cross_ss2d_x3_single_launch_vs_oracle(xf, shape):
+    """xfs_cross_ss2d_x3: three SS2D streams (one parameter set, own x / delta / Bs, ONE shared Cs) in one forward and one
+    backward launch, against the oracle run stream by stream; the shared-Cs and parameter gradients sum over the streams
+    (models/fusion_vmamba.py:536-538, 567-569)."""
+    from xfmamba_b200 import _lib, fusion_ops
+    Bsz, D, N, H, W = shape
+    L = H * W
+    rng = np.random.default_rng(abs(hash(shape)) % 2**32)
+    cs = [_rand_ss2d(rng, Bsz, D, N, H, W) for _ in range(3)]
+    shared = {k: cs[0][k] for k in ("A", "Cs", "Ds", "delta_bias")}
+    assert fusion_ops.cross_ss2d_x3_supported(N, H, W)
+    lv = [{k: t(c[k]).requires_grad_(True) for k in ("x", "delta", "Bs")} for c in cs]
+    sh = {k: t(v).requires_grad_(True) for k, v in shared.items()}
+    before = _lib.launch_count()
+    ys = fusion_ops.cross_ss2d_x3([v["x"] for v in lv], [v["delta"] for v in lv], [v["Bs"] for v in lv], sh["Cs"], sh["A"], sh["Ds"],
+                                  sh["delta_bias"])
+    sum((y * t(c["dy"])).sum() for y, c in zip(ys, cs)).backward()
+    assert _lib.launch_count() - before == 2           # one forward kernel, one backward kernel
+    tot = {k: 0.0 for k in ("A", "Cs", "Ds", "delta_bias")}
+    for y, c, v in zip(ys, cs, lv):
+        args = (c["x"], c["delta"], shared["A"], c["Bs"], shared["Cs"], shared["Ds"], shared["delta_bias"])
+        assert rel_err(n(y), oracle.ss2d_fwd(*args, True, "f64")) < TOL32
+        gx, gd, gA, gB, gC, gD, gb = oracle.ss2d_bwd(*args, c["dy"], True, "f64")
+        assert rel_err(n(v["x"].grad), gx) < TOL32 and rel_err(n(v["delta"].grad), gd) < TOL32 and rel_err(n(v["Bs"].grad), gB) < TOL32
+        for k, gr in (("A", gA), ("Cs", gC), ("Ds", gD), ("delta_bias", gb)):
+            tot[k] = tot[k] + gr
+    for k in tot:
+        assert rel_err(n(sh[k].grad), tot[k]) < TOL32, k
+
+
+@pytest.mark.parametrize("shape", [(2, 6, 16, 49), (1, 5, 4, 12), (2, 130, 16, 49), (1, 3, 1, 64)])
+def test_swap_scan_fused_vs_oracle(xf, shape):
+    """xfs_swap_scan_fused: SwappingScan + S6 (K = 2) + SwappingMerge in one kernel, forward and the as-written backward
+    (models/fusion_vmamba.py:189-241, 812, 831-835), against the oracle's three-step composition."""
+    from xfmamba_b200 import _lib, fusion_ops
+    Bsz, D, N, L = shape
+    rng = np.random.default_rng(abs(hash(shape)) % 2**32)
+    f = lambda *s_: rng.standard_normal(s_, dtype=np.float32)
+    r = lambda *s_: rng.random(s_, dtype=np.float32)
+    c = dict(x=f(Bsz, D, L), x2=f(Bsz, D, L), delta=0.5 * r(Bsz, 2 * D, L), A=-0.5 * r(2 * D, N), Bs=f(Bsz, 2, N, L), Cs=f(Bsz, 2, N, L),
+             Ds=f(2 * D), delta_bias=0.5 * r(2 * D), dy=f(Bsz, D, L), dy2=f(Bsz, D, L))
+    lv = {k: t(v).requires_grad_(True) for k, v in c.items() if k not in ("dy", "dy2")}
+    before = _lib.launch_count()
+    y, y2 = fusion_ops.swap_scan_fused(lv["x"], lv["x2"], lv["delta"], lv["A"], lv["Bs"], lv["Cs"], lv["Ds"], lv["delta_bias"])
+    ((y * t(c["dy"])).sum() + (y2 * t(c["dy2"])).sum()).backward()
+    assert _lib.launch_count() - before == 2
+    xs = oracle.swap_scan(c["x"], c["x2"]).reshape(Bsz, 2 * D, L)
+    ys = oracle.selective_scan_fwd(xs, c["delta"], c["A"], c["Bs"], c["Cs"], c["Ds"], c["delta_bias"], True, "f64")
+    ry, ry2 = oracle.swap_merge(ys.reshape(Bsz, 2, D, L))
+    assert rel_err(n(y), ry) < TOL32 and rel_err(n(y2), ry2) < TOL32
+    dout = np.stack([c["dy"], c["dy2"]], axis=1).reshape(Bsz, 2 * D, L)              # SwappingMerge.backward: stack
+    du, dd, dA, dB, dC, dD, db = oracle.selective_scan_bwd(xs, c["delta"], c["A"], c["Bs"], c["Cs"], c["Ds"], c["delta_bias"], dout, True, "f64")
+    du = du.reshape(Bsz, 2, D, L)                                                    # SwappingScan.backward as written: halves
+    for k, gr in (("x", du[:, 0]), ("x2", du[:, 1]), ("delta", dd), ("A", dA), ("Bs", dB), ("Cs", dC), ("Ds", dD), ("delta_bias", db)):
+        assert rel_err(n(lv[k].grad), gr) < TOL32, k
+
+
 def test_native_library_was_used(xf):
     """the driver checks which .so the test process loaded; make the launch counter prove it too"""
     from xfmamba_b200 import _lib

@@ -81,6 +81,8 @@ def test_logits_match_reference_on_cpu_with_oracle_ops(golden, monkeypatch):
     m.eval()
     for name in ("ss2d_scan", "cross_scan_fn", "selective_scan_fn", "swapping_scan", "swapping_merge", "layer_norm_2d", "dwconv3x3_silu", "dt_proj"):
         monkeypatch.setattr(M.OPS, name, getattr(OracleOps, name))
+    monkeypatch.setattr(M.OPS, "cross_ss2d_x3", None)
+    monkeypatch.setattr(M.OPS, "swap_scan_fused", None)
     with torch.no_grad():
         logits = m(torch.from_numpy(g["xa"]), torch.from_numpy(g["xb"]))
     assert rel_err(logits.numpy(), g["logits"]) < 1e-4
@@ -172,6 +174,8 @@ def _oracle_ops(monkeypatch):
     import xfmamba_b200.model as M
     for name in ("ss2d_scan", "cross_scan_fn", "selective_scan_fn", "swapping_scan", "swapping_merge", "layer_norm_2d", "dwconv3x3_silu", "dt_proj"):
         monkeypatch.setattr(M.OPS, name, getattr(OracleOps, name))
+    monkeypatch.setattr(M.OPS, "cross_ss2d_x3", None)
+    monkeypatch.setattr(M.OPS, "swap_scan_fused", None)
 
 
 def test_shallow_fusion_core_golden_on_cpu(golden, monkeypatch):

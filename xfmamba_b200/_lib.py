@@ -48,6 +48,43 @@ class Ss2dBwdArgs(ctypes.Structure):
                [(n, c_i32) for n in ("dtype", "dout_dtype", "delta_softplus", "scans", "acc_replicas", "reserved")]
 
 
+_P3 = c_vp * 3
+
+
+class X3FwdArgs(ctypes.Structure):
+    _fields_ = [(n, _P3) for n in ("x", "delta", "Bs", "Cs", "y", "states")] + [(n, c_vp) for n in ("A", "Ds", "delta_bias")] + \
+               [(n, c_i64) for n in ("batch", "D", "N", "H", "W")] + \
+               [(n, c_i32) for n in ("dtype", "out_dtype", "delta_softplus", "nstreams")]
+
+
+class X3BwdArgs(ctypes.Structure):
+    _fields_ = [(n, _P3) for n in ("x", "delta", "Bs", "Cs", "dy", "dx", "ddelta", "dBs", "dCs")] + \
+               [(n, c_vp) for n in ("A", "Ds", "delta_bias", "dA", "dDs", "ddelta_bias")] + \
+               [(n, c_i64) for n in ("batch", "D", "N", "H", "W")] + \
+               [(n, c_i32) for n in ("dtype", "dout_dtype", "delta_softplus", "nstreams")]
+
+
+class SwapFusedFwdArgs(ctypes.Structure):
+    _fields_ = [(n, c_vp) for n in ("x", "x2", "delta", "A", "Bs", "Cs", "Ds", "delta_bias", "y", "y2", "states")] + \
+               [(n, c_i64) for n in ("batch", "D", "N", "L")] + \
+               [(n, c_i32) for n in ("dtype", "out_dtype", "delta_softplus", "reserved")]
+
+
+class SwapFusedBwdArgs(ctypes.Structure):
+    _fields_ = [(n, c_vp) for n in ("x", "x2", "delta", "A", "Bs", "Cs", "Ds", "delta_bias", "dy", "dy2", "dx", "dx2", "ddelta",
+                                    "dA", "dBs", "dCs", "dDs", "ddelta_bias")] + \
+               [(n, c_i64) for n in ("batch", "D", "N", "L")] + \
+               [(n, c_i32) for n in ("dtype", "dout_dtype", "delta_softplus", "reserved")]
+
+
+def p3(tensors):
+    """three device pointers (missing / None entries stay NULL)"""
+    arr = _P3()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
 # every symbol include/xfscan.h declares (tests/test_cabi.py checks the .so exports all of them)
 SYMBOLS = [
     "xfs_version", "xfs_error_string", "xfs_device_ok", "xfs_chunk_len", "xfs_num_chunks", "xfs_launch_count",
@@ -55,6 +92,8 @@ SYMBOLS = [
     "xfs_selective_scan_fwd", "xfs_selective_scan_bwd", "xfs_ss2d_supported", "xfs_ss2d_fwd", "xfs_ss2d_bwd",
     "xfs_layernorm2d_fwd", "xfs_layernorm2d_bwd",
     "xfs_dwconv3x3_supported", "xfs_dwconv3x3_fwd", "xfs_dwconv3x3_bwd", "xfs_dt_proj_fwd",
+    "xfs_cross_ss2d_x3_supported", "xfs_cross_ss2d_x3_fwd", "xfs_cross_ss2d_x3_bwd",
+    "xfs_swap_scan_fused_supported", "xfs_swap_scan_fused_fwd", "xfs_swap_scan_fused_bwd",
 ]
 
 
@@ -96,6 +135,12 @@ def lib() -> ctypes.CDLL:
     L.xfs_dwconv3x3_fwd.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, ctypes.c_int, ctypes.c_int, c_vp]
     L.xfs_dwconv3x3_bwd.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, ctypes.c_int, ctypes.c_int, c_vp]
     L.xfs_dt_proj_fwd.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, ctypes.c_int, c_vp]
+    L.xfs_cross_ss2d_x3_supported.argtypes = [c_i64, c_i64, c_i64]
+    L.xfs_cross_ss2d_x3_fwd.argtypes = [ctypes.POINTER(X3FwdArgs), c_vp]
+    L.xfs_cross_ss2d_x3_bwd.argtypes = [ctypes.POINTER(X3BwdArgs), c_vp]
+    L.xfs_swap_scan_fused_supported.argtypes = [c_i64, c_i64]
+    L.xfs_swap_scan_fused_fwd.argtypes = [ctypes.POINTER(SwapFusedFwdArgs), c_vp]
+    L.xfs_swap_scan_fused_bwd.argtypes = [ctypes.POINTER(SwapFusedBwdArgs), c_vp]
     _lib = L
     return L
 

@@ -23,6 +23,12 @@ int ss2d_mid_supported(int64_t, int64_t, int64_t);
 int launch_ss2d_mid_fwd(const xfs_ss2d_fwd_args&, cudaStream_t);
 int launch_ss2d_mid_bwd(const xfs_ss2d_bwd_args&, cudaStream_t);
 
+int fusion_small_supported(int64_t, int64_t);
+int launch_cross_ss2d_x3_fwd(const xfs_cross_ss2d_x3_fwd_args&, cudaStream_t);
+int launch_cross_ss2d_x3_bwd(const xfs_cross_ss2d_x3_bwd_args&, cudaStream_t);
+int launch_swap_scan_fused_fwd(const xfs_swap_scan_fused_fwd_args&, cudaStream_t);
+int launch_swap_scan_fused_bwd(const xfs_swap_scan_fused_bwd_args&, cudaStream_t);
+
 int launch_ln2d_fwd(const void*, const float*, const float*, void*, float*, float*, int64_t, int64_t, int64_t, float, int, cudaStream_t);
 int launch_ln2d_bwd(const void*, const void*, const float*, const float*, const float*, void*, float*, float*, int64_t, int64_t, int64_t, int, cudaStream_t);
 
@@ -169,6 +175,51 @@ int xfs_ss2d_bwd(const xfs_ss2d_bwd_args* a, xfs_stream_t stream) {
     }
     if (!ss2d_supported(a->D, a->N, a->H, a->W, a->dtype, 1)) return XFS_ERR_UNSUPPORTED;
     return launch_ss2d_bwd(*a, (cudaStream_t)stream);
+}
+
+int xfs_cross_ss2d_x3_supported(int64_t N, int64_t H, int64_t W) { return H > 0 && W > 0 && fusion_small_supported(N, H * W); }
+
+int xfs_cross_ss2d_x3_fwd(const xfs_cross_ss2d_x3_fwd_args* a, xfs_stream_t stream) {
+    if (!a || !a->A) return XFS_ERR_NULL;
+    if (a->nstreams < 1 || a->nstreams > 3 || a->batch <= 0 || a->D <= 0 || a->N <= 0 || a->H <= 0 || a->W <= 0) return XFS_ERR_SHAPE;
+    for (int s = 0; s < a->nstreams; ++s)
+        if (!a->x[s] || !a->delta[s] || !a->Bs[s] || !a->Cs[s] || !a->y[s]) return XFS_ERR_NULL;
+    if (bad_dtype(a->dtype) || (a->out_dtype != XFS_F32 && a->out_dtype != a->dtype)) return XFS_ERR_DTYPE;
+    if (!fusion_small_supported(a->N, a->H * a->W)) return XFS_ERR_UNSUPPORTED;
+    return launch_cross_ss2d_x3_fwd(*a, (cudaStream_t)stream);
+}
+
+int xfs_cross_ss2d_x3_bwd(const xfs_cross_ss2d_x3_bwd_args* a, xfs_stream_t stream) {
+    if (!a || !a->A || !a->dA) return XFS_ERR_NULL;
+    if ((a->Ds != nullptr) != (a->dDs != nullptr) || (a->delta_bias != nullptr) != (a->ddelta_bias != nullptr)) return XFS_ERR_NULL;
+    if (a->nstreams < 1 || a->nstreams > 3 || a->batch <= 0 || a->D <= 0 || a->N <= 0 || a->H <= 0 || a->W <= 0) return XFS_ERR_SHAPE;
+    for (int s = 0; s < a->nstreams; ++s)
+        if (!a->x[s] || !a->delta[s] || !a->Bs[s] || !a->Cs[s] || !a->dy[s] || !a->dx[s] || !a->ddelta[s] || !a->dBs[s] || !a->dCs[s])
+            return XFS_ERR_NULL;
+    if (bad_dtype(a->dtype) || (a->dout_dtype != XFS_F32 && a->dout_dtype != a->dtype)) return XFS_ERR_DTYPE;
+    if (!fusion_small_supported(a->N, a->H * a->W)) return XFS_ERR_UNSUPPORTED;
+    return launch_cross_ss2d_x3_bwd(*a, (cudaStream_t)stream);
+}
+
+int xfs_swap_scan_fused_supported(int64_t N, int64_t L) { return fusion_small_supported(N, L); }
+
+int xfs_swap_scan_fused_fwd(const xfs_swap_scan_fused_fwd_args* a, xfs_stream_t stream) {
+    if (!a || !a->x || !a->x2 || !a->delta || !a->A || !a->Bs || !a->Cs || !a->y || !a->y2) return XFS_ERR_NULL;
+    if (a->batch <= 0 || a->D <= 0 || a->N <= 0 || a->L <= 0) return XFS_ERR_SHAPE;
+    if (bad_dtype(a->dtype) || (a->out_dtype != XFS_F32 && a->out_dtype != a->dtype)) return XFS_ERR_DTYPE;
+    if (!fusion_small_supported(a->N, a->L)) return XFS_ERR_UNSUPPORTED;
+    return launch_swap_scan_fused_fwd(*a, (cudaStream_t)stream);
+}
+
+int xfs_swap_scan_fused_bwd(const xfs_swap_scan_fused_bwd_args* a, xfs_stream_t stream) {
+    if (!a || !a->x || !a->x2 || !a->delta || !a->A || !a->Bs || !a->Cs || !a->dy || !a->dy2 || !a->dx || !a->dx2 || !a->ddelta ||
+        !a->dA || !a->dBs || !a->dCs)
+        return XFS_ERR_NULL;
+    if ((a->Ds != nullptr) != (a->dDs != nullptr) || (a->delta_bias != nullptr) != (a->ddelta_bias != nullptr)) return XFS_ERR_NULL;
+    if (a->batch <= 0 || a->D <= 0 || a->N <= 0 || a->L <= 0) return XFS_ERR_SHAPE;
+    if (bad_dtype(a->dtype) || (a->dout_dtype != XFS_F32 && a->dout_dtype != a->dtype)) return XFS_ERR_DTYPE;
+    if (!fusion_small_supported(a->N, a->L)) return XFS_ERR_UNSUPPORTED;
+    return launch_swap_scan_fused_bwd(*a, (cudaStream_t)stream);
 }
 
 int xfs_layernorm2d_fwd(const void* x, const float* weight, const float* bias, void* y, float* mean, float* rstd, int64_t B,

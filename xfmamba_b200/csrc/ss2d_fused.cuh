@@ -119,6 +119,31 @@ __device__ __forceinline__ float quad_sum(float v) {             // sum over the
     return v;
 }
 
+// stage kQuad channel images (L <= 64 each) into row-major / column-major swizzled rows of 64 floats.  The loads of a thread
+// are issued as one batch before its first shared-memory store (see staged_loop in fusion_small.cu for why).
+template <typename T>
+__device__ __forceinline__ void stage_quad(const T* __restrict__ base, int64_t chan_stride, int nvalid, float* bN, float* bT,
+                                           int H, int W, int L, int tid) {
+    constexpr int kIt = kQuad * kSmallL / 128;
+    float v[kIt];
+#pragma unroll
+    for (int u = 0; u < kIt; ++u) {
+        const int idx = tid + u * 128, ch = idx >> 6, p = idx & 63;
+        v[u] = (ch < nvalid && p < L) ? Elem<T>::to_f(base[ch * chan_stride + p]) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < kIt; ++u) {
+        const int idx = tid + u * 128, ch = idx >> 6, p = idx & 63;
+        bN[ch * kSmallL + swz_pos(p)] = v[u];
+        if (p < L) {
+            const int h = p / W, w = p - h * W;
+            bT[ch * kSmallL + swz_pos(w * H + h)] = v[u];
+        } else {
+            bT[ch * kSmallL + swz_pos(p)] = 0.0f;
+        }
+    }
+}
+
 inline size_t fwd_smem(int64_t L, int64_t N, int ch) {
     return sizeof(float) * (size_t)(4 * ch * buf_len(L) + (N == 1 ? 0 : 4 * ch * kFusedMaxState));
 }

@@ -12,24 +12,6 @@
 
 namespace xfs {
 
-// stage kQuad channel images (L <= 64 each) into row-major / column-major swizzled rows of 64 floats
-template <typename T>
-__device__ __forceinline__ void stage_quad(const T* __restrict__ base, int64_t chan_stride, int nvalid, float* bN, float* bT,
-                                           int H, int W, int L, int tid) {
-    for (int idx = tid; idx < kQuad * kSmallL; idx += 128) {
-        const int ch = idx >> 6, p = idx & 63;
-        float v = 0.0f;
-        if (ch < nvalid && p < L) v = Elem<T>::to_f(base[ch * chan_stride + p]);
-        bN[ch * kSmallL + swz_pos(p)] = v;
-        if (p < L) {
-            const int h = p / W, w = p - h * W;
-            bT[ch * kSmallL + swz_pos(w * H + h)] = v;
-        } else {
-            bT[ch * kSmallL + swz_pos(p)] = 0.0f;
-        }
-    }
-}
-
 // =========================================================================================================
 // forward
 // =========================================================================================================

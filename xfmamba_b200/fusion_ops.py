@@ -21,7 +21,8 @@ from .csm import cross_merge_raw, cross_scan_raw
 from .csms6s import _check_scan_args, selective_scan_bwd_raw, selective_scan_fwd_raw
 
 __all__ = ["SwappingScan_multiview", "SwappingMerge_multiview", "swapping_scan", "swapping_merge", "ss2d_scan",
-           "SS2DScanFn", "ss2d_fused_supported", "ss2d_fwd_raw", "ss2d_bwd_raw", "ss2d_acc_replicas"]
+           "SS2DScanFn", "ss2d_fused_supported", "ss2d_fwd_raw", "ss2d_bwd_raw", "ss2d_acc_replicas",
+           "cross_ss2d_x3", "cross_ss2d_x3_supported", "swap_scan_fused", "swap_scan_fused_supported"]
 
 
 def _swap_scan_raw(x, x2):
@@ -261,3 +262,143 @@ def ss2d_scan(x, delta, A, Bs, Cs, Ds=None, delta_bias=None, delta_softplus=True
         delta = delta.reshape(x.shape[0], 4 * x.shape[1], -1)
     need = _lib.grad_needed(x, delta, A, Bs, Cs, Ds, delta_bias)
     return SS2DScanFn.apply(x, delta, A, Bs, Cs, Ds, delta_bias, delta_softplus, oflex, need)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fusion blocks at their real shapes (L <= 64, N <= 16): single-launch kernels of csrc/fusion_small.cu
+# ---------------------------------------------------------------------------------------------------------------------
+def cross_ss2d_x3_supported(N, H, W) -> bool:
+    return bool(_lib.lib().xfs_cross_ss2d_x3_supported(int(N), int(H), int(W)))
+
+
+def swap_scan_fused_supported(N, L) -> bool:
+    return bool(_lib.lib().xfs_swap_scan_fused_supported(int(N), int(L)))
+
+
+class CrossSS2Dx3Fn(torch.autograd.Function):
+    """The three SS2D streams of Cross_SS2Dv5.forward_corev2 (models/fusion_vmamba.py:485-569) in one forward and one
+    backward launch.  Inputs: 3 x (x, delta, Bs), ONE Cs (the fused stream's, shared by all three, :536-538/:567-569), and the
+    shared A, Ds, delta_bias.  Returns the three merged outputs (B, D, L) fp32."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, x0, x1, x2, d0, d1, d2, B0, B1, B2, Cs, A, Ds, delta_bias, need_grad):
+        xs, ds, Bs = [x0, x1, x2], [d0, d1, d2], [B0, B1, B2]
+        dev = _lib.require_cuda(*xs, *ds, *Bs, Cs, A, Ds, delta_bias)
+        Bsz, D, H, W = x0.shape
+        L, N = H * W, Cs.shape[2]
+        xs = [t.contiguous() for t in xs]
+        ds = [t.reshape(Bsz, 4 * D, L).contiguous() for t in ds]
+        Bs = [t.contiguous() for t in Bs]
+        Cs, A = Cs.contiguous(), A.float().contiguous()
+        Ds = None if Ds is None else Ds.float().contiguous()
+        delta_bias = None if delta_bias is None else delta_bias.float().contiguous()
+        ys = [torch.empty((Bsz, D, L), dtype=torch.float32, device=dev) for _ in range(3)]
+        args = _lib.X3FwdArgs(_lib.p3(xs), _lib.p3(ds), _lib.p3(Bs), _lib.p3([Cs, Cs, Cs]), _lib.p3(ys), _lib.p3([None] * 3),
+                              _lib.ptr(A), _lib.ptr(Ds), _lib.ptr(delta_bias), Bsz, D, N, H, W,
+                              _lib.dtype_code(x0), _lib.F32, 1, 3)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().xfs_cross_ss2d_x3_fwd(args, _lib.stream(dev))
+        _lib.check(rc, "cross_ss2d_x3_fwd")
+        if need_grad:
+            ctx.has_D, ctx.has_bias = Ds is not None, delta_bias is not None
+            ctx.save_for_backward(*xs, *ds, *Bs, Cs, A, *[t for t in (Ds, delta_bias) if t is not None])
+        return tuple(ys)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, g0, g1, g2):
+        sv = list(ctx.saved_tensors)
+        xs, ds, Bs, Cs, A = sv[0:3], sv[3:6], sv[6:9], sv[9], sv[10]
+        rest = sv[11:]
+        Ds = rest.pop(0) if ctx.has_D else None
+        delta_bias = rest.pop(0) if ctx.has_bias else None
+        dev = xs[0].device
+        Bsz, D, H, W = xs[0].shape
+        L, N = H * W, Cs.shape[2]
+        gs = [(torch.zeros((Bsz, D, L), dtype=torch.float32, device=dev) if g is None else g.contiguous().float()) for g in (g0, g1, g2)]
+        dxs = [torch.empty_like(t) for t in xs]
+        dds = [torch.empty_like(t) for t in ds]
+        dBs = [torch.zeros(Bs[0].shape, dtype=torch.float32, device=dev) for _ in range(3)]
+        dCs = torch.zeros(Cs.shape, dtype=torch.float32, device=dev)
+        dA = torch.zeros_like(A)
+        dDs = None if Ds is None else torch.zeros_like(Ds)
+        dbias = None if delta_bias is None else torch.zeros_like(delta_bias)
+        args = _lib.X3BwdArgs(_lib.p3(xs), _lib.p3(ds), _lib.p3(Bs), _lib.p3([Cs, Cs, Cs]), _lib.p3(gs), _lib.p3(dxs), _lib.p3(dds),
+                              _lib.p3(dBs), _lib.p3([dCs, dCs, dCs]), _lib.ptr(A), _lib.ptr(Ds), _lib.ptr(delta_bias),
+                              _lib.ptr(dA), _lib.ptr(dDs), _lib.ptr(dbias), Bsz, D, N, H, W, _lib.dtype_code(xs[0]), _lib.F32, 1, 3)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().xfs_cross_ss2d_x3_bwd(args, _lib.stream(dev))
+        _lib.check(rc, "cross_ss2d_x3_bwd")
+        dt = Bs[0].dtype
+        return (*dxs, *dds, *[t.to(dt) for t in dBs], dCs.to(Cs.dtype), dA, dDs, dbias, None)
+
+
+def cross_ss2d_x3(xs, deltas, Bs, Cs, A, Ds=None, delta_bias=None):
+    """three SS2D streams sharing one parameter set and one Cs: (y0, y1, y2), each (B, D, H*W) fp32 (delta_softplus, oflex)"""
+    need = _lib.grad_needed(*xs, *deltas, *Bs, Cs, A, Ds, delta_bias)
+    return CrossSS2Dx3Fn.apply(*xs, *deltas, *Bs, Cs, A, Ds, delta_bias, need)
+
+
+class SwapScanFusedFn(torch.autograd.Function):
+    """SwappingScan_multiview + selective scan (K = 2) + SwappingMerge_multiview (models/fusion_vmamba.py:812, 831-835) in one
+    forward and one backward launch; the backward follows the reference as written (no un-swap, :217-221)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, x, x2, delta, A, Bs, Cs, Ds, delta_bias, need_grad):
+        dev = _lib.require_cuda(x, x2, delta, A, Bs, Cs, Ds, delta_bias)
+        Bsz, D = x.shape[:2]
+        L, N = x[0, 0].numel(), Bs.shape[2]
+        x, x2, Bs, Cs = x.contiguous(), x2.contiguous(), Bs.contiguous(), Cs.contiguous()
+        delta = delta.reshape(Bsz, 2 * D, L).contiguous()
+        A = A.float().contiguous()
+        Ds = None if Ds is None else Ds.float().contiguous()
+        delta_bias = None if delta_bias is None else delta_bias.float().contiguous()
+        y = torch.empty((Bsz, D, L), dtype=torch.float32, device=dev)
+        y2 = torch.empty_like(y)
+        args = _lib.SwapFusedFwdArgs(_lib.ptr(x), _lib.ptr(x2), _lib.ptr(delta), _lib.ptr(A), _lib.ptr(Bs), _lib.ptr(Cs), _lib.ptr(Ds),
+                                     _lib.ptr(delta_bias), _lib.ptr(y), _lib.ptr(y2), None, Bsz, D, N, L,
+                                     _lib.dtype_code(x), _lib.F32, 1, 0)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().xfs_swap_scan_fused_fwd(args, _lib.stream(dev))
+        _lib.check(rc, "swap_scan_fused_fwd")
+        if need_grad:
+            ctx.has_D, ctx.has_bias = Ds is not None, delta_bias is not None
+            ctx.save_for_backward(x, x2, delta, A, Bs, Cs, *[t for t in (Ds, delta_bias) if t is not None])
+        return y, y2
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gy, gy2):
+        sv = list(ctx.saved_tensors)
+        x, x2, delta, A, Bs, Cs = sv[:6]
+        rest = sv[6:]
+        Ds = rest.pop(0) if ctx.has_D else None
+        delta_bias = rest.pop(0) if ctx.has_bias else None
+        dev = x.device
+        Bsz, D = x.shape[:2]
+        L, N = x[0, 0].numel(), Bs.shape[2]
+        zero = lambda: torch.zeros((Bsz, D, L), dtype=torch.float32, device=dev)
+        gy = zero() if gy is None else gy.contiguous().float()
+        gy2 = zero() if gy2 is None else gy2.contiguous().float()
+        dx, dx2, ddelta = torch.empty_like(x), torch.empty_like(x2), torch.empty_like(delta)
+        dA = torch.zeros_like(A)
+        dBs = torch.zeros(Bs.shape, dtype=torch.float32, device=dev)
+        dCs = torch.zeros(Cs.shape, dtype=torch.float32, device=dev)
+        dDs = None if Ds is None else torch.zeros_like(Ds)
+        dbias = None if delta_bias is None else torch.zeros_like(delta_bias)
+        args = _lib.SwapFusedBwdArgs(_lib.ptr(x), _lib.ptr(x2), _lib.ptr(delta), _lib.ptr(A), _lib.ptr(Bs), _lib.ptr(Cs), _lib.ptr(Ds),
+                                     _lib.ptr(delta_bias), _lib.ptr(gy), _lib.ptr(gy2), _lib.ptr(dx), _lib.ptr(dx2), _lib.ptr(ddelta),
+                                     _lib.ptr(dA), _lib.ptr(dBs), _lib.ptr(dCs), _lib.ptr(dDs), _lib.ptr(dbias), Bsz, D, N, L,
+                                     _lib.dtype_code(x), _lib.F32, 1, 0)
+        with torch.cuda.device(dev):
+            rc = _lib.lib().xfs_swap_scan_fused_bwd(args, _lib.stream(dev))
+        _lib.check(rc, "swap_scan_fused_bwd")
+        return dx, dx2, ddelta, dA, dBs.to(Bs.dtype), dCs.to(Cs.dtype), dDs, dbias, None
+
+
+def swap_scan_fused(x, x2, delta, A, Bs, Cs, Ds=None, delta_bias=None):
+    """(y, y2), each (B, D, L) fp32 = SwappingMerge(selective_scan(SwappingScan(x, x2), delta, A, Bs, Cs, Ds, delta_bias, True))"""
+    need = _lib.grad_needed(x, x2, delta, A, Bs, Cs, Ds, delta_bias)
+    return SwapScanFusedFn.apply(x, x2, delta, A, Bs, Cs, Ds, delta_bias, need)

@@ -39,6 +39,9 @@ OPS = types.SimpleNamespace(
     layer_norm_2d=norm.layer_norm_2d,
     dwconv3x3_silu=conv.dwconv3x3_silu,
     dt_proj=proj.dt_proj,
+    # single-launch kernels of the fusion blocks (L <= 64, N <= 16); None = compose the operators above (CPU tests do)
+    cross_ss2d_x3=fusion_ops.cross_ss2d_x3,
+    swap_scan_fused=fusion_ops.swap_scan_fused,
 )
 
 VARIANTS = {   # reference net_fusionmamba.py:151-159
@@ -83,10 +86,14 @@ def shallow_fuse_core(x, x2, x_proj_weight, dt_projs_weight, dt_projs_bias, A_lo
     K, _, R = dt_projs_weight.shape
     N = A_logs.shape[1]
     L = H * W
-    xs = OPS.swapping_scan(x, x2)                                            # (B, 2, D, L)
+    xs = OPS.swapping_scan(x, x2)                                            # (B, 2, D, L): the operand of the x_proj GEMM
     x_dbl = torch.einsum("b k d l, k c d -> b k c l", xs, x_proj_weight)
     dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
     dts = OPS.dt_proj(dts, dt_projs_weight)
+    if getattr(OPS, "swap_scan_fused", None) is not None and x.is_cuda and fusion_ops.swap_scan_fused_supported(N, L):
+        # swap-gather + S6 + split in one kernel: u comes from x / x2 directly, the halves go straight to y / y2
+        return OPS.swap_scan_fused(x.view(B, D, L), x2.view(B, D, L), dts, -A_logs.float().exp(), Bs.contiguous(), Cs.contiguous(),
+                                   Ds.float(), dt_projs_bias.reshape(-1).float())
     ys = OPS.selective_scan_fn(xs.view(B, -1, L), dts, -A_logs.float().exp(), Bs.contiguous(),
                                Cs.contiguous(), Ds.float(), dt_projs_bias.reshape(-1).float(), True, True)
     return OPS.swapping_merge(ys.view(B, K, -1, L))
@@ -94,6 +101,19 @@ def shallow_fuse_core(x, x2, x_proj_weight, dt_projs_weight, dt_projs_bias, A_lo
 
 def cross_fuse_core(x, x2, x_fuse, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds):
     """(y, y2, y_fuse) each (B, D, L) fp32; the view streams use the fused stream's Cs (reference :536-538, 567-569)"""
+    B, D, H, W = x.shape
+    K, _, R = dt_projs_weight.shape
+    N = A_logs.shape[1]
+    if getattr(OPS, "cross_ss2d_x3", None) is not None and x.is_cuda and fusion_ops.cross_ss2d_x3_supported(N, H, W):
+        # one launch for the three streams: x_proj / dt_proj on the three images batched, then the x3 kernel
+        xcat = torch.cat([x_fuse, x, x2], dim=0)
+        dts_r, Bs, Cs = _route_small(xcat, x_proj_weight, K, R, N)
+        dts = OPS.dt_proj(dts_r, dt_projs_weight)                            # (3B, K*D, L)
+        d3, B3 = dts.view(3, B, K * D, H * W), Bs.reshape(3, B, K, N, H * W)
+        Cs_fuse = Cs.reshape(3, B, K, N, H * W)[0]
+        y_fuse, y, y2 = OPS.cross_ss2d_x3([x_fuse, x, x2], [d3[0], d3[1], d3[2]], [B3[0], B3[1], B3[2]], Cs_fuse,
+                                          -A_logs.float().exp(), Ds.float(), dt_projs_bias.reshape(-1).float())
+        return y, y2, y_fuse
     y_fuse, Cs_fuse = ss2d_core(x_fuse, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, return_Cs=True)
     y = ss2d_core(x, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, Cs_override=Cs_fuse)
     y2 = ss2d_core(x2, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, Cs_override=Cs_fuse)
