@@ -204,7 +204,7 @@ def run_ours(args):
 
     # reusable output buffers (device-resident leg)
     y = torch.empty((batch, w["D"], L), dtype=torch.float32, device=dev)
-    states = torch.empty((batch, 4 * w["D"], _lib.num_chunks(L), w["N"]), dtype=torch.float32, device=dev)
+    states = torch.empty((batch, 4 * w["D"], _lib.ss2d_states_len(w["N"], w["H"], w["W"], tdt, torch.float32)), dtype=torch.float32, device=dev)
     # dBs / dCs accumulators: replicated (see xfs_ss2d_bwd_args.acc_replicas), summed over the replicas inside ss2d_bwd_raw
     n_rep = fusion_ops.ss2d_acc_replicas(w["D"], L, batch)
     acc_shape = tuple(d["Bs"].shape) if n_rep == 1 else (n_rep,) + tuple(d["Bs"].shape)

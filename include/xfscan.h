@@ -147,7 +147,11 @@ XFS_API int xfs_selective_scan_bwd(const xfs_scan_bwd_args* a, xfs_stream_t stre
  *   x      : (batch, D, H, W) dtype                        delta : (batch, 4*D, H*W) dtype, in scan order of each route
  *   A      : (4*D, N) f32                                  Bs,Cs : (batch, 4, N, H*W) dtype, in scan order
  *   Ds, delta_bias : (4*D) f32 or NULL                     y     : (batch, D, H*W) out_dtype, spatial order
- *   states : (batch, 4*D, xfs_num_chunks(H*W), N) f32 (nullable in fwd)
+ *   states : (batch, 4*D, xfs_ss2d_states_len(N, H, W, dtype, out_dtype)) f32 (nullable in fwd): checkpoints of the
+ *            recurrence written by fwd and read by bwd.  One state per 256-position chunk and n (xfs_num_chunks(H*W) * N
+ *            floats per row) in general; one state per LANE and chunk (32 per chunk) on the path that serves the
+ *            backbone shapes (f32 rows, N == 1, H*W % 4 == 0, H*W > 256) -- there every tensor must be 16-byte
+ *            aligned (XFS_ERR_ALIGN otherwise).  The layout is private to the fwd / bwd pair.
  * bwd: dy (batch, D, H*W) dout_dtype -> dx (batch, D, H, W) dtype, ddelta (batch, 4*D, H*W) dtype, and the
  *   accumulated f32 dA, dBs, dCs, dDs, ddelta_bias as for xfs_selective_scan_bwd.
  * Returns XFS_ERR_UNSUPPORTED when the per-channel working set does not fit in shared memory
@@ -194,6 +198,7 @@ typedef struct {
 } xfs_ss2d_bwd_args;
 
 XFS_API int xfs_ss2d_supported(int64_t D, int64_t N, int64_t H, int64_t W, int dtype, int backward);
+XFS_API int64_t xfs_ss2d_states_len(int64_t N, int64_t H, int64_t W, int dtype, int out_dtype);   /* floats per (batch, 4*D) row */
 XFS_API int xfs_ss2d_fwd(const xfs_ss2d_fwd_args* a, xfs_stream_t stream);
 XFS_API int xfs_ss2d_bwd(const xfs_ss2d_bwd_args* a, xfs_stream_t stream);
 

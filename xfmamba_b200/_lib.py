@@ -89,7 +89,7 @@ def p3(tensors):
 SYMBOLS = [
     "xfs_version", "xfs_error_string", "xfs_device_ok", "xfs_chunk_len", "xfs_num_chunks", "xfs_launch_count",
     "xfs_cross_scan", "xfs_cross_merge", "xfs_swap_scan", "xfs_swap_merge", "xfs_swap_stack",
-    "xfs_selective_scan_fwd", "xfs_selective_scan_bwd", "xfs_ss2d_supported", "xfs_ss2d_fwd", "xfs_ss2d_bwd",
+    "xfs_selective_scan_fwd", "xfs_selective_scan_bwd", "xfs_ss2d_supported", "xfs_ss2d_states_len", "xfs_ss2d_fwd", "xfs_ss2d_bwd",
     "xfs_layernorm2d_fwd", "xfs_layernorm2d_bwd",
     "xfs_dwconv3x3_supported", "xfs_dwconv3x3_fwd", "xfs_dwconv3x3_bwd", "xfs_dt_proj_fwd",
     "xfs_cross_ss2d_x3_supported", "xfs_cross_ss2d_x3_fwd", "xfs_cross_ss2d_x3_bwd",
@@ -127,6 +127,8 @@ def lib() -> ctypes.CDLL:
     L.xfs_selective_scan_fwd.argtypes = [ctypes.POINTER(ScanFwdArgs), c_vp]
     L.xfs_selective_scan_bwd.argtypes = [ctypes.POINTER(ScanBwdArgs), c_vp]
     L.xfs_ss2d_supported.argtypes = [c_i64, c_i64, c_i64, c_i64, ctypes.c_int, ctypes.c_int]
+    L.xfs_ss2d_states_len.restype = c_i64
+    L.xfs_ss2d_states_len.argtypes = [c_i64, c_i64, c_i64, ctypes.c_int, ctypes.c_int]
     L.xfs_ss2d_fwd.argtypes = [ctypes.POINTER(Ss2dFwdArgs), c_vp]
     L.xfs_ss2d_bwd.argtypes = [ctypes.POINTER(Ss2dBwdArgs), c_vp]
     L.xfs_layernorm2d_fwd.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, ctypes.c_float, ctypes.c_int, c_vp]
@@ -183,6 +185,11 @@ def stream(dev: torch.device):
 
 def num_chunks(L: int) -> int:
     return int(lib().xfs_num_chunks(int(L)))
+
+
+def ss2d_states_len(N: int, H: int, W: int, dtype, out_dtype) -> int:
+    """floats per (batch, 4*D) row of the fused SS2D checkpoints (layout private to the fwd / bwd kernel pair)"""
+    return int(lib().xfs_ss2d_states_len(int(N), int(H), int(W), _DTYPES[dtype], _DTYPES[out_dtype]))
 
 
 def launch_count() -> int:

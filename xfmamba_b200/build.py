@@ -19,7 +19,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 SO = PKG / "libxfscan.so"
 OBJ = PKG / "build"
-SOURCES = ["routes.cu", "selective_scan.cu", "ss2d_fwd.cu", "ss2d_bwd.cu", "ss2d_ring_fwd.cu", "fusion_small.cu", "ss2d_small.cu", "ss2d_mid.cu", "layernorm2d.cu", "dwconv.cu", "dtproj.cu", "capi.cu"]
+SOURCES = ["routes.cu", "selective_scan.cu", "ss2d_fwd.cu", "ss2d_bwd.cu", "ss2d_ring_fwd.cu", "ss2d_lane_bwd.cu", "fusion_small.cu", "ss2d_small.cu", "ss2d_mid.cu", "layernorm2d.cu", "dwconv.cu", "dtproj.cu", "capi.cu"]
 HEADERS = [CSRC / "xfscan_common.cuh", CSRC / "ss2d_tiles.cuh", CSRC / "ss2d_fused.cuh", CSRC / "ss2d_ring.cuh", PKG.parent / "include" / "xfscan.h"]
 
 NVCC_FLAGS = [
@@ -33,7 +33,7 @@ NVCC_FLAGS = [
 # --use_fast_math (ftz, approximate division / sqrt / exp) only for the scan translation units, whose transcendental code is
 # written with explicit approx PTX anyway and is held to the oracle by the parity tests.  The routes (documented as bit exact,
 # including fp32 denormals), LayerNorm2d (rstd) and the depthwise convolution (SiLU / sigmoid backward) use IEEE arithmetic.
-FAST_MATH = {"selective_scan.cu", "ss2d_fwd.cu", "ss2d_bwd.cu", "ss2d_ring_fwd.cu", "fusion_small.cu", "ss2d_ring_bwd.cu", "ss2d_small.cu", "ss2d_mid.cu",
+FAST_MATH = {"selective_scan.cu", "ss2d_fwd.cu", "ss2d_bwd.cu", "ss2d_ring_fwd.cu", "ss2d_lane_bwd.cu", "ss2d_small.cu", "ss2d_mid.cu",
              "fusion_small.cu"}
 
 

@@ -23,6 +23,9 @@ int ss2d_mid_supported(int64_t, int64_t, int64_t);
 int launch_ss2d_mid_fwd(const xfs_ss2d_fwd_args&, cudaStream_t);
 int launch_ss2d_mid_bwd(const xfs_ss2d_bwd_args&, cudaStream_t);
 
+int ss2d_lane_states(int64_t, int64_t, int64_t, int, int);
+int launch_ss2d_lane_bwd(const xfs_ss2d_bwd_args&, cudaStream_t);
+
 int fusion_small_supported(int64_t, int64_t);
 int launch_cross_ss2d_x3_fwd(const xfs_cross_ss2d_x3_fwd_args&, cudaStream_t);
 int launch_cross_ss2d_x3_bwd(const xfs_cross_ss2d_x3_bwd_args&, cudaStream_t);
@@ -144,6 +147,14 @@ int xfs_ss2d_supported(int64_t D, int64_t N, int64_t H, int64_t W, int dtype, in
     return ss2d_small_supported(N, H, W) || ss2d_supported(D, N, H, W, dtype, backward);
 }
 
+int64_t xfs_ss2d_states_len(int64_t N, int64_t H, int64_t W, int dtype, int out_dtype) {
+    if (N <= 0 || H <= 0 || W <= 0) return 0;
+    const int64_t nch = (H * W + kChunk - 1) / kChunk;
+    const bool small = ss2d_small_supported(N, H, W), mid = !small && ss2d_mid_supported(N, H, W);
+    if (!small && !mid && ss2d_lane_states(N, H, W, dtype, out_dtype)) return nch * 32;     // one state per lane and chunk
+    return nch * N;
+}
+
 int xfs_ss2d_fwd(const xfs_ss2d_fwd_args* a, xfs_stream_t stream) {
     if (!a || !a->x || !a->delta || !a->A || !a->Bs || !a->Cs || !a->y) return XFS_ERR_NULL;
     if (a->batch <= 0 || a->D <= 0 || a->N <= 0 || a->H <= 0 || a->W <= 0) return XFS_ERR_SHAPE;
@@ -154,7 +165,11 @@ int xfs_ss2d_fwd(const xfs_ss2d_fwd_args* a, xfs_stream_t stream) {
         const int rc = launch_ss2d_mid_fwd(*a, (cudaStream_t)stream);
         if (rc != XFS_ERR_UNSUPPORTED) return rc;
     }
-    if (ss2d_ring_fwd_supported(*a)) return launch_ss2d_ring_fwd(*a, (cudaStream_t)stream);   // TMA-fed kernel (N = 1, fp32)
+    // TMA-fed kernel (N = 1, fp32).  It writes LANE-granular checkpoints (xfs_ss2d_states_len), which only
+    // ss2d_lane_bwd.cu reads: with checkpoints requested it runs exactly when that backward will.
+    const bool lane_states = ss2d_lane_states(a->N, a->H, a->W, a->dtype, a->out_dtype);
+    if (ss2d_ring_fwd_supported(*a) && (a->states == nullptr || lane_states)) return launch_ss2d_ring_fwd(*a, (cudaStream_t)stream);
+    if (a->states != nullptr && lane_states) return XFS_ERR_ALIGN;      // shape of the lane-checkpoint path, misaligned rows
     if (!ss2d_supported(a->D, a->N, a->H, a->W, a->dtype, 0)) return XFS_ERR_UNSUPPORTED;
     return launch_ss2d_fwd(*a, (cudaStream_t)stream);
 }
@@ -173,6 +188,7 @@ int xfs_ss2d_bwd(const xfs_ss2d_bwd_args* a, xfs_stream_t stream) {
         const int rc = launch_ss2d_mid_bwd(*a, (cudaStream_t)stream);
         if (rc != XFS_ERR_UNSUPPORTED) return rc;
     }
+    if (ss2d_lane_states(a->N, a->H, a->W, a->dtype, a->dout_dtype)) return launch_ss2d_lane_bwd(*a, (cudaStream_t)stream);
     if (!ss2d_supported(a->D, a->N, a->H, a->W, a->dtype, 1)) return XFS_ERR_UNSUPPORTED;
     return launch_ss2d_bwd(*a, (cudaStream_t)stream);
 }

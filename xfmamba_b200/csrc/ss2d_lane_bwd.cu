@@ -1,0 +1,393 @@
+// ss2d_lane_bwd.cu -- fused SS2D backward for the shapes XFMamba's backbone spends its bytes on (N == 1, fp32 rows,
+// 16-byte aligned, L % 4 == 0, more than one chunk), written around LANE-GRANULAR checkpoints.
+//
+// Same decomposition as ss2d_bwd.cu (CTA = one (batch, channel) image, warp k = CrossScan route k, six position-indexed
+// image buffers, pair protocol for the du accumulators), but the forward kernel (ss2d_ring_fwd.cu) saves the state
+// ENTERING every lane's 8 positions instead of one state per 256-position chunk (+0.5 B per (b,k,d,l) on 24 / 44).  With
+// that the backward needs no forward re-scan across lanes: each lane replays its 8 positions with one FMA per position
+// (h_i = a_i h_{i-1} + b_i), and only the adjoint  g_i = C_i dy_i + a_{i+1} g_{i+1}  still crosses lanes -- ONE
+// warp-shuffle scan per chunk instead of two, no prefix products of the forward maps, two short dependent chains
+// instead of two 8-deep affine folds.  Per (b,k,d,l): 4 MUFU (ex2, lg2, rcp, ex2), ~10 packed FFMA2/FMUL2/FADD2,
+// 3 scalar chain operations, 3.75 for the adjoint scan.  Formulas as in ss2d_bwd.cu / selective_scan.cu:
+//     du = D dy + g dt B      ddt = g (B u + A (h - b))      ddelta = ddt * sigmoid(delta + bias)
+//     dA += g dt (h - b)      dB = g dt u                     dC = dy h          (b = dt B u, h - b = a h_prev)
+// The reference computes the same quantities per thread-block chunk (selective_scan_bwd_kernel.cuh:126-274).
+#include "ss2d_ring.cuh"
+
+namespace xfs {
+using namespace ring;
+
+#ifndef XFS_LANE_DIAG
+#define XFS_LANE_DIAG 0          // timing experiments only: bit 0 = no dB / dC reductions, bit 1 = no ddelta stores
+#endif
+
+namespace {
+
+// All per-position arrays of the chunk loop are kept in MEMORY order (index 0 = lowest address of the lane's 8 elements
+// of a streamed row), as four packed pairs.  Rows are stored in scan order, so memory order IS the route's forward scan
+// order for all four routes: the replay chain runs over ascending indices, the adjoint over descending ones, and the
+// ddelta / dB / dC results come out in store order.  Only the operands held in shared memory are position-indexed:
+// for a flipped route memory element i is position 7 - i, i.e. pair q is pair 3 - q of the position-ordered granules
+// with its halves swapped -- register renaming plus the HI_LO operand modifier of FFMA2 / FMUL2 / FADD2, no moves.
+__device__ __forceinline__ f2 swp(const f2 v) { return make_float2(v.y, v.x); }
+template <bool kRev>
+__device__ __forceinline__ void reorder(const f2 (&v)[4], f2 (&o)[4]) {       // position order <-> memory order (an involution)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[q] = kRev ? swp(v[3 - q]) : v[q];
+}
+__device__ __forceinline__ void unpack(const float4 g0, const float4 g1, f2 (&o)[4]) {
+    o[0] = make_float2(g0.x, g0.y); o[1] = make_float2(g0.z, g0.w); o[2] = make_float2(g1.x, g1.y); o[3] = make_float2(g1.z, g1.w);
+}
+
+__device__ __forceinline__ float& el(f2 (&v)[4], int i) { return (i & 1) ? v[i >> 1].y : v[i >> 1].x; }
+
+__device__ __forceinline__ float4 ldg128(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void stg128(float* p, f2 lo, f2 hi) {
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(lo.x), "f"(lo.y), "f"(hi.x), "f"(hi.y) : "memory");
+}
+
+struct LaneChunk {              // streamed operands of one chunk, as loaded (memory order)
+    float4 dt0, dt1, B0, B1, C0, C1;
+    float hin;
+};
+
+}  // namespace
+
+template <bool kSoftplus>
+__global__ void __launch_bounds__(128, 3)
+ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
+    extern __shared__ __align__(16) float smem[];
+    const int H = (int)p.H, W = (int)p.W, L = H * W;
+    const int Lb = (int)buf_len(L);
+    const int nch = (L + kChunk - 1) / kChunk;
+    const int D = (int)p.D;
+    // batch index fastest (see ss2d_bwd.cu): resident CTAs belong to different images, so their dB / dC rows differ
+    const int b = blockIdx.x % (int)p.batch;
+    const int d = blockIdx.x / (int)p.batch;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int k = __shfl_sync(kFull, tid >> 5, 0);                  // warp k = route k (provably warp-uniform)
+    const bool transposed = k & 1;
+
+    float* xN = smem;
+    float* xT = xN + Lb;
+    float* gN = xT + Lb;
+    float* gT = gN + Lb;
+    float* dN = gT + Lb;
+    float* dT = dN + Lb;
+
+    const int kd = k * D + d;
+    const int64_t row = ((int64_t)b * 4 * D + kd) * L;
+    const int64_t bc = ((int64_t)b * 4 + k) * L;
+    const int rep = p.acc_replicas > 1 ? d % p.acc_replicas : 0;
+    const int64_t acc = (((int64_t)rep * p.batch + b) * 4 + k) * L;
+    const float* __restrict__ dt_row = reinterpret_cast<const float*>(p.delta) + row;
+    float* __restrict__ ddt_row = reinterpret_cast<float*>(p.ddelta) + row;
+    const float* __restrict__ B_row = reinterpret_cast<const float*>(p.Bs) + bc;
+    const float* __restrict__ C_row = reinterpret_cast<const float*>(p.Cs) + bc;
+    float* __restrict__ dB_row = p.dBs + acc;
+    float* __restrict__ dC_row = p.dCs + acc;
+    const float* __restrict__ st_row = p.states + ((int64_t)b * 4 * D + kd) * ((int64_t)nch * 32);
+    // keep the seven row pointers in registers: left to itself the compiler re-derives them (64-bit multiplies) in every chunk
+    asm volatile("" : "+l"(dt_row), "+l"(ddt_row), "+l"(B_row), "+l"(C_row), "+l"(dB_row), "+l"(dC_row), "+l"(st_row));
+
+    const float bias = p.delta_bias ? p.delta_bias[kd] : 0.0f;
+    const float bias_l2 = bias * kLog2e;
+    const float Dd = p.Ds ? p.Ds[kd] : 0.0f;
+    const float An = p.A[kd];
+    const float A2 = An * kLog2e;
+
+    // byte offsets of the lane's two granules inside a 1 KB chunk of a position-indexed (swizzled) image buffer
+    const int f4l = (2 * lane) ^ ((lane >> 2) & 7);
+    const uint32_t offA = (uint32_t)f4l * 16u, offB = (uint32_t)(f4l ^ 1) * 16u;
+    const uint32_t xb = s32(transposed ? xT : xN), gb = s32(transposed ? gT : gN), db = s32(transposed ? dT : dN);
+
+    // last chunk (the only one with positions >= L): which granules exist
+    const int s0_last = (nch - 1) * kChunk + 8 * lane;
+    const bool ok_lo = s0_last + 4 <= L, ok_hi = s0_last + 8 <= L;      // positions s0..s0+3 / s0+4..s0+7
+    const bool in_buf_last = s0_last < Lb;
+
+    const int m = nch / 2;             // routes 2/3 first touch chunks [0, m) of the du accumulators, routes 0/1 [m, nch)
+
+    auto walk = [&](auto rev_tag) __attribute__((always_inline)) {
+        constexpr bool kRev = decltype(rev_tag)::value;            // forward scan direction of the route: descending position
+        // which of the lane's two granules (memory order) exist in the last chunk
+        const bool okm0 = kRev ? ok_hi : ok_lo, okm1 = kRev ? ok_lo : ok_hi;
+
+        // Both directions walk the rows towards LOWER addresses: routes 0/1 chunks nch-1 -> 0 (address = position), routes
+        // 2/3 chunks 0 -> nch-1 (address = L-1 - position).  off = element offset of the granule at the lower address.
+        int off = kRev ? L - 8 - 8 * lane : (nch - 1) * kChunk + 8 * lane;
+        int soff = (kRev ? 0 : (nch - 1) * 32) + lane;     // checkpoint [j][lane] of the chunk being loaded
+        const unsigned off_max = (unsigned)(L - 4), soff_max = (unsigned)((nch - 1) * 32 + lane);
+        // L2 prefetch ahead of the register loads: lanes 0-7 / 8-15 / 16-23 take the 128-byte lines of the dt / B / C chunk
+        // rows (lanes 24-31 start so far below zero that their offset never turns non-negative)
+        const float* pf_row = lane < 8 ? dt_row : (lane < 16 ? B_row : C_row);
+        int pf_off = lane < 24 ? (kRev ? L - kChunk : (nch - 1) * kChunk) + (lane & 7) * 32 : -(1 << 30);      // walk step 0
+
+        auto load = [&](LaneChunk& c) __attribute__((always_inline)) {
+            // Granules outside the row (last chunk; the re-load after the final chunk) are read from a valid aligned offset
+            // instead -- ONE unsigned min per granule covers both ends -- and callers neutralise what they hold.
+            const unsigned o0 = min((unsigned)off, off_max), o1 = min((unsigned)(off + 4), off_max);
+            c.dt0 = ldg128(dt_row + o0); c.dt1 = ldg128(dt_row + o1);
+            c.B0 = ldg128(B_row + o0); c.B1 = ldg128(B_row + o1);
+            c.C0 = ldg128(C_row + o0); c.C1 = ldg128(C_row + o1);
+            c.hin = __ldg(st_row + min((unsigned)soff, soff_max));
+            off -= kChunk;
+            soff += kRev ? 32 : -32;
+        };
+        auto prefetch = [&]() __attribute__((always_inline)) {
+            pf_off -= kChunk;
+            if (pf_off >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_row + pf_off));
+        };
+
+        LaneChunk c;
+        load(c);                        // in flight while the images are staged
+        prefetch();                     // walk steps 1 and 2; every chunk then prefetches the step three ahead of it
+        prefetch();
+        {
+            const float* __restrict__ x = reinterpret_cast<const float*>(p.x) + ((int64_t)b * D + d) * L;
+            const float* __restrict__ dyp = reinterpret_cast<const float*>(p.dy) + ((int64_t)b * D + d) * L;
+            stage_image<float>(x, xN, xT, H, W, L, Lb, true, tid, 128);
+            stage_image<float>(dyp, gN, gT, H, W, L, Lb, true, tid, 128);
+            cta_barrier();
+        }
+
+        f2 dD2 = splat2(0.0f), dbias2 = splat2(0.0f), dA2 = splat2(0.0f);
+        float qcarry = 0.0f;
+
+        auto chunk = [&](uint32_t ib, auto last_tag, auto first_tag) __attribute__((always_inline)) {
+            constexpr bool LAST = decltype(last_tag)::value;       // chunk nch-1: may hold positions >= L
+            constexpr bool FIRST = decltype(first_tag)::value;     // first touch of the pair's du accumulator: plain stores
+            // ---- shared-memory operands: position order in the buffers, memory order (u, dy) for the arithmetic
+            f2 u[4], dy[4], dyp[4];
+            {
+                float4 uA = make_float4(0.f, 0.f, 0.f, 0.f), uB = uA, gA = uA, gB = uA;
+                if (!LAST || in_buf_last) {
+                    uA = lds128(xb + ib + offA); uB = lds128(xb + ib + offB);
+                    gA = lds128(gb + ib + offA); gB = lds128(gb + ib + offB);
+                }
+                f2 up[4];
+                unpack(uA, uB, up);
+                unpack(gA, gB, dyp);
+                reorder<kRev>(up, u);
+                reorder<kRev>(dyp, dy);
+            }
+            // ---- consume the streamed registers: dt -> log2-scaled argument, C -> C dy, B -> B u and (after softplus) dt B
+            f2 xr[4], Bv[4], Cv[4], xl[4], cd[4], Bu[4];
+            unpack(c.dt0, c.dt1, xr);
+            unpack(c.B0, c.B1, Bv);
+            unpack(c.C0, c.C1, Cv);
+            const float hin = c.hin;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                xl[i] = kSoftplus ? fma2(xr[i], splat2(kLog2e), splat2(bias_l2)) : add2(xr[i], splat2(bias));
+                cd[i] = mul2(Cv[i], dy[i]);
+                Bu[i] = mul2(Bv[i], u[i]);
+            }
+            f2 dt[4], sig[4], dtB[4];
+            if (kSoftplus) {
+                f2 e2[4], w[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    e2[i] = make_float2(ex2(xl[i].x), ex2(xl[i].y));
+                    w[i] = add2(e2[i], splat2(1.0f));
+                    dt[i] = mul2(make_float2(lg2(w[i].x), lg2(w[i].y)), splat2(kLn2));
+                    sig[i] = mul2(e2[i], make_float2(rcp(w[i].x), rcp(w[i].y)));     // sigmoid(x) = e / (1 + e)
+                }
+                // chunk-uniform test: does any element need the small-argument series or the x > 20 identity?
+                const bool odd = !(min8(e2) >= kEMin && max8(e2) <= kEMax);
+                if (__any_sync(kFull, odd)) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const f2 x = add2(xr[i], splat2(bias)), e = e2[i];
+                        f2 ser = fma2(e, splat2(-0.25f), splat2(0.33333334f));
+                        ser = fma2(ser, e, splat2(-0.5f));
+                        ser = fma2(ser, e, splat2(1.0f));
+                        ser = mul2(ser, e);
+                        f2 r;
+                        r.x = (e.x < kEMin) ? ser.x : dt[i].x;
+                        r.y = (e.y < kEMin) ? ser.y : dt[i].y;
+                        dt[i].x = (x.x > 20.0f) ? x.x : r.x;
+                        dt[i].y = (x.y > 20.0f) ? x.y : r.y;
+                        sig[i].x = (x.x > 20.0f) ? 1.0f : sig[i].x;
+                        sig[i].y = (x.y > 20.0f) ? 1.0f : sig[i].y;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { dt[i] = xl[i]; sig[i] = splat2(1.0f); }
+            }
+            if (LAST) {     // positions >= L: identity maps (dt = 0); their u / dy are 0 in the buffers
+                if (!okm0) { dt[0] = dt[1] = splat2(0.0f); }
+                if (!okm1) { dt[2] = dt[3] = splat2(0.0f); }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dtB[i] = mul2(dt[i], Bv[i]);
+
+            // every streamed register has been read: re-load them with the next chunk (unconditionally -- the step after
+            // the last re-reads clamped offsets), then one L2 prefetch further ahead
+            load(c);
+            prefetch();
+
+            // ---- forward replay from the lane checkpoint (h_i = a_i h_prev + b_i) and the adjoint fold against it
+            // (G_i = cd_i + a_{i+1} G_{i+1} with zero entering, Pq_i = a_{i+1} ... a_7, so that g_i = G_i + Pq_i r_in)
+            f2 h[4], G[4], Pq[4], hp[4];
+            float Pl, Sl;
+            {
+                f2 a[4], bu[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const f2 ar = mul2(dt[i], splat2(A2));
+                    a[i] = make_float2(ex2(ar.x), ex2(ar.y));
+                    bu[i] = mul2(dtB[i], u[i]);
+                }
+                float prev = hin;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    prev = fmaf(el(a, i), prev, el(bu, i));
+                    el(h, i) = prev;
+                }
+                float Gp = el(cd, 7), Pp = 1.0f;
+                el(G, 7) = Gp; el(Pq, 7) = 1.0f;
+#pragma unroll
+                for (int i = 6; i >= 0; --i) {
+                    const float an = el(a, i + 1);
+                    Gp = fmaf(an, Gp, el(cd, i));
+                    Pp = (i == 6) ? an : Pp * an;
+                    el(G, i) = Gp;
+                    el(Pq, i) = Pp;
+                }
+                Pl = el(a, 0) * Pp; Sl = el(a, 0) * Gp;          // the lane's map r_in -> a_0 g_0
+#pragma unroll
+                for (int i = 0; i < 4; ++i) hp[i] = fma2(bu[i], splat2(-1.0f), h[i]);       // a_i h_prev
+            }
+            // ---- everything that does not depend on the adjoint: dC, dD, and the coefficients g will be multiplied with
+            const int o = off + 2 * kChunk;        // this chunk's offset (`off` has moved on twice: this chunk's load and the re-load)
+            const bool st0 = !LAST || okm0, st1 = !LAST || okm1;
+            f2 ts[4], dthp[4], dtu[4];
+            {
+                f2 dCv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    dCv[i] = mul2(dy[i], h[i]);
+                    dD2 = fma2(dy[i], u[i], dD2);
+                    ts[i] = mul2(fma2(splat2(An), hp[i], Bu[i]), sig[i]);       // ddelta = g ts
+                    dthp[i] = mul2(dt[i], hp[i]);                               // dA += g dthp
+                    dtu[i] = mul2(dt[i], u[i]);                                 // dB = g dtu
+                }
+                if ((XFS_LANE_DIAG & 4) && !LAST) {      // experiment: TMA bulk reduction from (aliased!) shared memory
+                    const uint32_t lo_ = (uint32_t)(kRev ? 248 - 8 * lane : 8 * lane) * 4u;
+                    sts128(gb + ib + lo_, make_float4(dCv[0].x, dCv[0].y, dCv[1].x, dCv[1].y));
+                    sts128(gb + ib + lo_ + 16, make_float4(dCv[2].x, dCv[2].y, dCv[3].x, dCv[3].y));
+                }
+                if (!(XFS_LANE_DIAG & 1) && st0) red_add_v4(dC_row + o, dCv[0].x, dCv[0].y, dCv[1].x, dCv[1].y);
+                if (!(XFS_LANE_DIAG & 1) && st1) red_add_v4(dC_row + o + 4, dCv[2].x, dCv[2].y, dCv[3].x, dCv[3].y);
+            }
+            // ---- the adjoint across lanes: ONE warp scan per chunk, against the forward direction
+            float q_out;
+            const float r_in = warp_prefix_p<!kRev>(Pl, Sl, qcarry, lane, q_out);
+            qcarry = q_out;
+
+            f2 g[4], dd[4], dBv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                g[i] = fma2(Pq[i], splat2(r_in), G[i]);
+                dd[i] = mul2(g[i], ts[i]);
+                dBv[i] = mul2(g[i], dtu[i]);
+                dA2 = fma2(g[i], dthp[i], dA2);
+                dbias2 = add2(dbias2, dd[i]);          // dt = 0 beyond L makes these terms exactly 0 (h_prev = 0 or g = 0 there)
+            }
+            if (!(XFS_LANE_DIAG & 2) && st0) stg128(ddt_row + o, dd[0], dd[1]);
+            if (!(XFS_LANE_DIAG & 2) && st1) stg128(ddt_row + o + 4, dd[2], dd[3]);
+            if ((XFS_LANE_DIAG & 4) && !LAST) {
+                const uint32_t lo_ = (uint32_t)(kRev ? 248 - 8 * lane : 8 * lane) * 4u;
+                sts128(xb + ib + lo_, make_float4(dBv[0].x, dBv[0].y, dBv[1].x, dBv[1].y));
+                sts128(xb + ib + lo_ + 16, make_float4(dBv[2].x, dBv[2].y, dBv[3].x, dBv[3].y));
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    const int cstart = o - (kRev ? 248 - 8 * lane : 8 * lane);
+                    bulk_red_add_f32(dB_row + cstart, xb + ib, 1024u);
+                    bulk_red_add_f32(dC_row + cstart, gb + ib, 1024u);
+                    bulk_commit();
+                }
+            }
+            if (!(XFS_LANE_DIAG & 1) && st0) red_add_v4(dB_row + o, dBv[0].x, dBv[0].y, dBv[1].x, dBv[1].y);
+            if (!(XFS_LANE_DIAG & 1) && st1) red_add_v4(dB_row + o + 4, dBv[2].x, dBv[2].y, dBv[3].x, dBv[3].y);
+            // ---- du = D dy + g dt B into the pair's accumulator (position order: operands re-read with swapped halves)
+            if (!LAST || in_buf_last) {
+                f2 gp[4], dtBp[4], du[4];
+                reorder<kRev>(g, gp);
+                reorder<kRev>(dtB, dtBp);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) du[i] = fma2(gp[i], dtBp[i], mul2(splat2(Dd), dyp[i]));
+                float4 vA = make_float4(du[0].x, du[0].y, du[1].x, du[1].y), vB = make_float4(du[2].x, du[2].y, du[3].x, du[3].y);
+                if (!FIRST) { vA = add4(vA, lds128(db + ib + offA)); vB = add4(vB, lds128(db + ib + offB)); }
+                sts128(db + ib + offA, vA);
+                sts128(db + ib + offB, vB);
+            }
+        };
+
+        const std::true_type T{};
+        const std::false_type F{};
+        if (!kRev) {                   // chunks nch-1 -> 0; first touches [m, nch)
+            uint32_t ib = (uint32_t)(nch - 1) * (kChunk * 4);
+            chunk(ib, T, T);
+            int j = nch - 2;
+#pragma unroll 1
+            for (; j >= m; --j) { ib -= kChunk * 4; chunk(ib, F, T); }
+            pair_barrier(k & 1);
+#pragma unroll 1
+            for (; j >= 0; --j) { ib -= kChunk * 4; chunk(ib, F, F); }
+        } else {                       // chunks 0 -> nch-1; first touches [0, m)
+            uint32_t ib = 0;
+            int j = 0;
+#pragma unroll 1
+            for (; j < m; ++j) { chunk(ib, F, T); ib += kChunk * 4; }
+            pair_barrier(k & 1);
+#pragma unroll 1
+            for (; j < nch - 1; ++j) { chunk(ib, F, F); ib += kChunk * 4; }
+            chunk(ib, T, F);
+        }
+
+        // parameter gradients of this route
+        const float vA = warp_sum(dA2.x + dA2.y), vD = warp_sum(dD2.x + dD2.y), vb = warp_sum(dbias2.x + dbias2.y);
+        if (lane == 0) {
+            atomicAdd(p.dA + kd, vA);
+            if (p.dDs) atomicAdd(p.dDs + kd, vD);
+            if (p.ddelta_bias) atomicAdd(p.ddelta_bias + kd, vb);
+        }
+    };
+    if (k >= 2) walk(std::true_type{}); else walk(std::false_type{});
+    __syncthreads();
+
+    // dx[p] = dN[p] + dT[w*H + h]   (CrossScanF.backward = cross-merge of du, models/csm_triton.py:208-225)
+    merge_out<float>(reinterpret_cast<float*>(p.dx) + ((int64_t)b * D + d) * L, dN, dT, H, W, tid, 128);
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------
+bool ring_enabled();
+
+// lane-granular checkpoints are what ss2d_ring_fwd.cu writes and this kernel reads; both sides decide with this predicate
+int ss2d_lane_states(int64_t N, int64_t H, int64_t W, int dtype, int out_dtype) {
+    const int64_t L = H * W;
+    return ring_enabled() && dtype == XFS_F32 && out_dtype == XFS_F32 && N == 1 && L % 4 == 0 && L > kChunk &&
+           bwd_smem(L, 1, 1) <= kSmemLimit;
+}
+
+int launch_ss2d_lane_bwd(const xfs_ss2d_bwd_args& a, cudaStream_t st) {
+    if (!(aligned16(a.x) && aligned16(a.delta) && aligned16(a.Bs) && aligned16(a.Cs) && aligned16(a.dy) && aligned16(a.dx) &&
+          aligned16(a.ddelta) && aligned16(a.dBs) && aligned16(a.dCs)))
+        return XFS_ERR_ALIGN;
+    const size_t smem = bwd_smem(a.H * a.W, 1, 1);
+    const unsigned grid = (unsigned)(a.batch * a.D);
+    if (a.delta_softplus) {
+        if (int rc = set_smem(ss2d_lane_bwd_kernel<true>, smem)) return rc;
+        ss2d_lane_bwd_kernel<true><<<grid, 128, smem, st>>>(a);
+    } else {
+        if (int rc = set_smem(ss2d_lane_bwd_kernel<false>, smem)) return rc;
+        ss2d_lane_bwd_kernel<false><<<grid, 128, smem, st>>>(a);
+    }
+    return check_launch();
+}
+
+}  // namespace xfs

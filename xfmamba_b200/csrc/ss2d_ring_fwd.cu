@@ -146,8 +146,10 @@ ss2d_ring_fwd_kernel(const xfs_ss2d_fwd_args p) {
     // touched by the forward route, [m, nch) by its flip: each route first-touches during its first n_first steps.
     const int m = (nch + 1) / 2;
     const int n_first = rev ? nch - m : m;
-    float* st_ptr = p.states ? p.states + ((int64_t)b * 4 * D + kd) * nch + (rev ? nch - 1 : 0) : nullptr;   // checkpoint of the chunk
-    const int st_inc = rev ? -1 : 1;
+    // LANE-GRANULAR checkpoints for ss2d_lane_bwd.cu: row (b, k*D+d) holds nch x 32 floats, entry [j][lane] = the state
+    // ENTERING the 8 positions of lane `lane` of position-order chunk j, in the route's scan direction
+    float* st_ptr = p.states ? p.states + ((int64_t)b * 4 * D + kd) * ((int64_t)nch * 32) + (rev ? (nch - 1) * 32 : 0) + lane : nullptr;
+    const int st_inc = rev ? -32 : 32;
     float carry = 0.0f;
 
     auto chunk = [&](int step, uint32_t ib, auto rev_tag, auto last_tag, auto first_tag) __attribute__((always_inline)) {
@@ -239,7 +241,7 @@ ss2d_ring_fwd_kernel(const xfs_ss2d_fwd_args p) {
         else h_in = warp_prefix<R>(PA * PB, o.a_first ? fmaf(PB, SA, SB) : fmaf(PA, SB, SA), carry, lane, h_out);
         carry = h_out;
         if (st_ptr) {
-            if (lane == 0) *st_ptr = h_out;
+            *st_ptr = h_in;
             st_ptr += st_inc;
         }
         const f2 hA = splat2(o.a_first ? h_in : fmaf(PB, h_in, SB));
@@ -324,6 +326,12 @@ int launch_ss2d_ring_fwd(const xfs_ss2d_fwd_args& a, cudaStream_t st) {
     static const int diag = [] { const char* e = std::getenv("XFS_RING_DIAG"); return e ? std::atoi(e) : 0; }();
     switch (diag) {
         case 1: return launch_ring_fwd_k<true, 1>(a, st);
+        case 2: return launch_ring_fwd_k<true, 2>(a, st);
+        case 4: return launch_ring_fwd_k<true, 4>(a, st);
+        case 8: return launch_ring_fwd_k<true, 8>(a, st);
+        case 16: return launch_ring_fwd_k<true, 16>(a, st);
+        case 6: return launch_ring_fwd_k<true, 6>(a, st);
+        case 14: return launch_ring_fwd_k<true, 14>(a, st);
         case 3: return launch_ring_fwd_k<true, 3>(a, st);
         case 5: return launch_ring_fwd_k<true, 5>(a, st);
         case 9: return launch_ring_fwd_k<true, 9>(a, st);

@@ -216,6 +216,40 @@ __device__ __forceinline__ float warp_prefix(float P, float S, float carry, int 
     return first ? carry : prev;
 }
 
+// Same scan; the "is there a lane `off` away" predicate of every step comes out of the shuffle itself (shfl.sync's
+// predicate destination) instead of an integer compare per step.
+template <bool kRev>
+__device__ __forceinline__ float warp_prefix_p(float P, float S, float carry, int lane, float& chunk_out) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        if (kRev)
+            asm volatile("{\n\t.reg .pred p;\n\t.reg .f32 pn, sn;\n\t"
+                         "shfl.sync.down.b32 pn|p, %0, %2, 0x1f, 0xffffffff;\n\t"
+                         "shfl.sync.down.b32 sn, %1, %2, 0x1f, 0xffffffff;\n\t"
+                         "@p fma.rn.ftz.f32 %1, %0, sn, %1;\n\t"
+                         "@p mul.ftz.f32 %0, %0, pn;\n\t}"
+                         : "+f"(P), "+f"(S) : "r"(off));
+        else
+            asm volatile("{\n\t.reg .pred p;\n\t.reg .f32 pn, sn;\n\t"
+                         "shfl.sync.up.b32 pn|p, %0, %2, 0, 0xffffffff;\n\t"
+                         "shfl.sync.up.b32 sn, %1, %2, 0, 0xffffffff;\n\t"
+                         "@p fma.rn.ftz.f32 %1, %0, sn, %1;\n\t"
+                         "@p mul.ftz.f32 %0, %0, pn;\n\t}"
+                         : "+f"(P), "+f"(S) : "r"(off));
+    }
+    const float incl = fmaf(P, carry, S);
+    chunk_out = __shfl_sync(kFull, incl, kRev ? 0 : 31);
+    float prev = carry;
+    if (kRev)
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .f32 t;\n\tshfl.sync.down.b32 t|p, %1, 1, 0x1f, 0xffffffff;\n\t@p mov.f32 %0, t;\n\t}"
+                     : "+f"(prev) : "f"(incl));
+    else
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .f32 t;\n\tshfl.sync.up.b32 t|p, %1, 1, 0, 0xffffffff;\n\t@p mov.f32 %0, t;\n\t}"
+                     : "+f"(prev) : "f"(incl));
+    (void)lane;
+    return prev;
+}
+
 // Two independent scans in one pass -- the forward re-scan along the walk direction kRev and the adjoint scan against
 // it, as the backward needs them for every chunk.  Shuffles are ordered with respect to each other, so two back-to-back
 // warp_prefix calls serialise their 7 round trips each; interleaved, the rounds of one hide the latency of the other.

@@ -124,7 +124,7 @@ def ss2d_fwd_raw(x, delta, A, Bs, Cs, Ds, delta_bias, delta_softplus=True, out_d
     if y is None:
         y = torch.empty((Bsz, D, L), dtype=out_dtype, device=dev)
     if states is None and need_states:
-        states = torch.empty((Bsz, 4 * D, _lib.num_chunks(L), N), dtype=torch.float32, device=dev)
+        states = torch.empty((Bsz, 4 * D, _lib.ss2d_states_len(N, H, W, x.dtype, y.dtype)), dtype=torch.float32, device=dev)
     if y.numel():
         args = _lib.Ss2dFwdArgs(_lib.ptr(x), _lib.ptr(delta), _lib.ptr(A), _lib.ptr(Bs), _lib.ptr(Cs), _lib.ptr(Ds),
                                 _lib.ptr(delta_bias), _lib.ptr(y), _lib.ptr(states), Bsz, D, N, H, W,
