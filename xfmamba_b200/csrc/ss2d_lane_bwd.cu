@@ -183,35 +183,22 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
                 cd[i] = mul2(Cv[i], dy[i]);
                 Bu[i] = mul2(Bv[i], u[i]);
             }
-            f2 dt[4], sig[4], dtB[4];
+            // The re-load of the streamed registers must be ISSUED here, most of a chunk ahead of its first use.  ptxas sinks
+            // independent loads to the end of a basic block (it did: ncu showed the load latency exposed at the top of every
+            // chunk), but not across a branch -- so everything that reads B / C / dt of this chunk, and the loads of the next
+            // one, sit in front of the (rare) branch that repairs softplus outliers; that branch re-reads B from L2.
+            f2 dt[4], sig[4], dtB[4], e2[4];
+            bool odd = false;
             if (kSoftplus) {
-                f2 e2[4], w[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     e2[i] = make_float2(ex2(xl[i].x), ex2(xl[i].y));
-                    w[i] = add2(e2[i], splat2(1.0f));
-                    dt[i] = mul2(make_float2(lg2(w[i].x), lg2(w[i].y)), splat2(kLn2));
-                    sig[i] = mul2(e2[i], make_float2(rcp(w[i].x), rcp(w[i].y)));     // sigmoid(x) = e / (1 + e)
+                    const f2 w = add2(e2[i], splat2(1.0f));
+                    dt[i] = mul2(make_float2(lg2(w.x), lg2(w.y)), splat2(kLn2));
+                    sig[i] = mul2(e2[i], make_float2(rcp(w.x), rcp(w.y)));     // sigmoid(x) = e / (1 + e)
                 }
                 // chunk-uniform test: does any element need the small-argument series or the x > 20 identity?
-                const bool odd = !(min8(e2) >= kEMin && max8(e2) <= kEMax);
-                if (__any_sync(kFull, odd)) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const f2 x = add2(xr[i], splat2(bias)), e = e2[i];
-                        f2 ser = fma2(e, splat2(-0.25f), splat2(0.33333334f));
-                        ser = fma2(ser, e, splat2(-0.5f));
-                        ser = fma2(ser, e, splat2(1.0f));
-                        ser = mul2(ser, e);
-                        f2 r;
-                        r.x = (e.x < kEMin) ? ser.x : dt[i].x;
-                        r.y = (e.y < kEMin) ? ser.y : dt[i].y;
-                        dt[i].x = (x.x > 20.0f) ? x.x : r.x;
-                        dt[i].y = (x.y > 20.0f) ? x.y : r.y;
-                        sig[i].x = (x.x > 20.0f) ? 1.0f : sig[i].x;
-                        sig[i].y = (x.y > 20.0f) ? 1.0f : sig[i].y;
-                    }
-                }
+                odd = !(min8(e2) >= kEMin && max8(e2) <= kEMax);
             } else {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { dt[i] = xl[i]; sig[i] = splat2(1.0f); }
@@ -222,11 +209,34 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) dtB[i] = mul2(dt[i], Bv[i]);
-
-            // every streamed register has been read: re-load them with the next chunk (unconditionally -- the step after
-            // the last re-reads clamped offsets), then one L2 prefetch further ahead
+            const int o = off + kChunk;            // this chunk's offset (`off` points at the next chunk until the re-load)
             load(c);
             prefetch();
+            if (kSoftplus && __any_sync(kFull, odd)) {
+                f2 Br[4];
+                unpack(ldg128(B_row + min((unsigned)o, off_max)), ldg128(B_row + min((unsigned)(o + 4), off_max)), Br);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const f2 x = mul2(xl[i], splat2(kLn2)), e = e2[i];       // delta + bias again
+                    f2 ser = fma2(e, splat2(-0.25f), splat2(0.33333334f));
+                    ser = fma2(ser, e, splat2(-0.5f));
+                    ser = fma2(ser, e, splat2(1.0f));
+                    ser = mul2(ser, e);
+                    f2 r;
+                    r.x = (e.x < kEMin) ? ser.x : dt[i].x;
+                    r.y = (e.y < kEMin) ? ser.y : dt[i].y;
+                    dt[i].x = (x.x > 20.0f) ? x.x : r.x;
+                    dt[i].y = (x.y > 20.0f) ? x.y : r.y;
+                    sig[i].x = (x.x > 20.0f) ? 1.0f : sig[i].x;
+                    sig[i].y = (x.y > 20.0f) ? 1.0f : sig[i].y;
+                }
+                if (LAST) {
+                    if (!okm0) { dt[0] = dt[1] = splat2(0.0f); }
+                    if (!okm1) { dt[2] = dt[3] = splat2(0.0f); }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dtB[i] = mul2(dt[i], Br[i]);
+            }
 
             // ---- forward replay from the lane checkpoint (h_i = a_i h_prev + b_i) and the adjoint fold against it
             // (G_i = cd_i + a_{i+1} G_{i+1} with zero entering, Pq_i = a_{i+1} ... a_7, so that g_i = G_i + Pq_i r_in)
@@ -261,7 +271,6 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
                 for (int i = 0; i < 4; ++i) hp[i] = fma2(bu[i], splat2(-1.0f), h[i]);       // a_i h_prev
             }
             // ---- everything that does not depend on the adjoint: dC, dD, and the coefficients g will be multiplied with
-            const int o = off + 2 * kChunk;        // this chunk's offset (`off` has moved on twice: this chunk's load and the re-load)
             const bool st0 = !LAST || okm0, st1 = !LAST || okm1;
             f2 ts[4], dthp[4], dtu[4];
             {
@@ -273,11 +282,6 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
                     ts[i] = mul2(fma2(splat2(An), hp[i], Bu[i]), sig[i]);       // ddelta = g ts
                     dthp[i] = mul2(dt[i], hp[i]);                               // dA += g dthp
                     dtu[i] = mul2(dt[i], u[i]);                                 // dB = g dtu
-                }
-                if ((XFS_LANE_DIAG & 4) && !LAST) {      // experiment: TMA bulk reduction from (aliased!) shared memory
-                    const uint32_t lo_ = (uint32_t)(kRev ? 248 - 8 * lane : 8 * lane) * 4u;
-                    sts128(gb + ib + lo_, make_float4(dCv[0].x, dCv[0].y, dCv[1].x, dCv[1].y));
-                    sts128(gb + ib + lo_ + 16, make_float4(dCv[2].x, dCv[2].y, dCv[3].x, dCv[3].y));
                 }
                 if (!(XFS_LANE_DIAG & 1) && st0) red_add_v4(dC_row + o, dCv[0].x, dCv[0].y, dCv[1].x, dCv[1].y);
                 if (!(XFS_LANE_DIAG & 1) && st1) red_add_v4(dC_row + o + 4, dCv[2].x, dCv[2].y, dCv[3].x, dCv[3].y);
@@ -298,19 +302,6 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
             }
             if (!(XFS_LANE_DIAG & 2) && st0) stg128(ddt_row + o, dd[0], dd[1]);
             if (!(XFS_LANE_DIAG & 2) && st1) stg128(ddt_row + o + 4, dd[2], dd[3]);
-            if ((XFS_LANE_DIAG & 4) && !LAST) {
-                const uint32_t lo_ = (uint32_t)(kRev ? 248 - 8 * lane : 8 * lane) * 4u;
-                sts128(xb + ib + lo_, make_float4(dBv[0].x, dBv[0].y, dBv[1].x, dBv[1].y));
-                sts128(xb + ib + lo_ + 16, make_float4(dBv[2].x, dBv[2].y, dBv[3].x, dBv[3].y));
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    const int cstart = o - (kRev ? 248 - 8 * lane : 8 * lane);
-                    bulk_red_add_f32(dB_row + cstart, xb + ib, 1024u);
-                    bulk_red_add_f32(dC_row + cstart, gb + ib, 1024u);
-                    bulk_commit();
-                }
-            }
             if (!(XFS_LANE_DIAG & 1) && st0) red_add_v4(dB_row + o, dBv[0].x, dBv[0].y, dBv[1].x, dBv[1].y);
             if (!(XFS_LANE_DIAG & 1) && st1) red_add_v4(dB_row + o + 4, dBv[2].x, dBv[2].y, dBv[3].x, dBv[3].y);
             // ---- du = D dy + g dt B into the pair's accumulator (position order: operands re-read with swapped halves)
@@ -371,7 +362,7 @@ bool ring_enabled();
 int ss2d_lane_states(int64_t N, int64_t H, int64_t W, int dtype, int out_dtype) {
     const int64_t L = H * W;
     return ring_enabled() && dtype == XFS_F32 && out_dtype == XFS_F32 && N == 1 && L % 4 == 0 && L > kChunk &&
-           bwd_smem(L, 1, 1) <= kSmemLimit;
+           bwd_smem(L, 1, 1) <= kSmemLimit && ring_fwd_smem(L, 1, 2) <= kSmemLimit;
 }
 
 int launch_ss2d_lane_bwd(const xfs_ss2d_bwd_args& a, cudaStream_t st) {

@@ -250,6 +250,45 @@ __device__ __forceinline__ float warp_prefix_p(float P, float S, float carry, in
     return prev;
 }
 
+// kN independent scans of the same direction, step by step interleaved (the round trips of one hide behind the others').
+// carry[] enters the chunk and is replaced by the state leaving it; in[] receives the state entering each lane.
+template <bool kRev, int kN>
+__device__ __forceinline__ void warp_prefix_pn(float (&P)[kN], float (&S)[kN], float (&carry)[kN], float (&in)[kN]) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+#pragma unroll
+        for (int n = 0; n < kN; ++n) {
+            if (kRev)
+                asm volatile("{\n\t.reg .pred p;\n\t.reg .f32 pn, sn;\n\t"
+                             "shfl.sync.down.b32 pn|p, %0, %2, 0x1f, 0xffffffff;\n\t"
+                             "shfl.sync.down.b32 sn, %1, %2, 0x1f, 0xffffffff;\n\t"
+                             "@p fma.rn.ftz.f32 %1, %0, sn, %1;\n\t"
+                             "@p mul.ftz.f32 %0, %0, pn;\n\t}"
+                             : "+f"(P[n]), "+f"(S[n]) : "r"(off));
+            else
+                asm volatile("{\n\t.reg .pred p;\n\t.reg .f32 pn, sn;\n\t"
+                             "shfl.sync.up.b32 pn|p, %0, %2, 0, 0xffffffff;\n\t"
+                             "shfl.sync.up.b32 sn, %1, %2, 0, 0xffffffff;\n\t"
+                             "@p fma.rn.ftz.f32 %1, %0, sn, %1;\n\t"
+                             "@p mul.ftz.f32 %0, %0, pn;\n\t}"
+                             : "+f"(P[n]), "+f"(S[n]) : "r"(off));
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < kN; ++n) {
+        const float incl = fmaf(P[n], carry[n], S[n]);
+        float prev = carry[n];
+        if (kRev)
+            asm volatile("{\n\t.reg .pred p;\n\t.reg .f32 t;\n\tshfl.sync.down.b32 t|p, %1, 1, 0x1f, 0xffffffff;\n\t@p mov.f32 %0, t;\n\t}"
+                         : "+f"(prev) : "f"(incl));
+        else
+            asm volatile("{\n\t.reg .pred p;\n\t.reg .f32 t;\n\tshfl.sync.up.b32 t|p, %1, 1, 0, 0xffffffff;\n\t@p mov.f32 %0, t;\n\t}"
+                         : "+f"(prev) : "f"(incl));
+        carry[n] = __shfl_sync(kFull, incl, kRev ? 0 : 31);
+        in[n] = prev;
+    }
+}
+
 // Two independent scans in one pass -- the forward re-scan along the walk direction kRev and the adjoint scan against
 // it, as the backward needs them for every chunk.  Shuffles are ordered with respect to each other, so two back-to-back
 // warp_prefix calls serialise their 7 round trips each; interleaved, the rounds of one hide the latency of the other.
