@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(name="ss2d_stage1_fwd_bwd", H=56, W=56, D=192, N=1, K=4)
 FWD_KERNEL = "ss2d_ring_fwd_kernel"     # what xfs_ss2d_fwd / xfs_ss2d_bwd launch for this workload in fp32 (profiles/traffic.json keys)
-BWD_KERNEL = "ss2d_bwd_kernel"
+BWD_KERNEL = "ss2d_lane_bwd_kernel"
 FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 

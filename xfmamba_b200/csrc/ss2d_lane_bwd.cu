@@ -42,8 +42,94 @@ __device__ __forceinline__ void unpack(const float4 g0, const float4 g1, f2 (&o)
 __device__ __forceinline__ float& el(f2 (&v)[4], int i) { return (i & 1) ? v[i >> 1].y : v[i >> 1].x; }
 
 __device__ __forceinline__ float4 ldg128(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// The streamed loads as VOLATILE asm: the compiler keeps them, in program order, in front of the warp vote that follows
+// them in the chunk body, and ptxas does not sink a load below the branch that ends its basic block.
+__device__ __forceinline__ float4 ldg128_pinned(const float* p) {
+    float4 v;
+    asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ldg32_pinned(const float* p) {
+    float v;
+    asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void stg128(float* p, f2 lo, f2 hi) {
     asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(lo.x), "f"(lo.y), "f"(hi.x), "f"(hi.y) : "memory");
+}
+
+// dB / dC reductions in FULL 32-byte sectors.  A lane's 8 values are one sector, but red.global.add takes 16 bytes per lane:
+// issued per lane the two instructions each touch HALF of 32 sectors, and the L1 sends every half-filled sector to L2 (ncu:
+// 77 M reduction sectors for 38.5 M sectors of payload, 73 % of all bytes the kernel pushes through the L1->L2 crossbar).  Lanes
+// 2q and 2q+1 therefore swap one granule (4 shuffles), so that the first instruction covers the even lanes' sectors completely
+// and the second the odd lanes'.  `step` = offset of lane l+1 relative to lane l (+8 / -8 elements).
+template <int kStep>
+__device__ __forceinline__ void red_sector_pair(float* __restrict__ row, int o, int lane, const f2 (&v)[4]) {
+    const bool odd = lane & 1;
+    const f2 s0 = odd ? v[0] : v[2], s1 = odd ? v[1] : v[3];          // even lanes send their high granule, odd their low one
+    f2 r0, r1;
+    r0.x = __shfl_xor_sync(kFull, s0.x, 1); r0.y = __shfl_xor_sync(kFull, s0.y, 1);
+    r1.x = __shfl_xor_sync(kFull, s1.x, 1); r1.y = __shfl_xor_sync(kFull, s1.y, 1);
+    const f2 a0 = odd ? r0 : v[0], a1 = odd ? r1 : v[1];              // even lane's sector: its low granule + (odd lane) its high one
+    const f2 b0 = odd ? v[2] : r0, b1 = odd ? v[3] : r1;              // odd lane's sector: (even lane) its low granule + its high one
+    red_add_v4(row + (odd ? o - kStep + 4 : o), a0.x, a0.y, a1.x, a1.y);
+    red_add_v4(row + (odd ? o + 4 : o + kStep), b0.x, b0.y, b1.x, b1.y);
+}
+
+// x and dy images -> row-major and column-major swizzled copies, with ALL global loads of a thread's blocks (two 4x4 blocks
+// of both images: 16 x 16 bytes) in flight before the first shared-memory store: one exposed memory round trip per CTA
+// instead of four (ncu: 12 % of the kernel's stall samples sat on the first store after each batch of four loads).
+__device__ __forceinline__ void stage_two_images(const float* __restrict__ x, const float* __restrict__ dy, float* xN, float* xT,
+                                                 float* gN, float* gT, int H, int W, int L, int Lb, int tid) {
+    // small images only (measured: 28x28 -3 %, 56x56 +2 %: there the four serial batches overlap with the other CTAs' walks)
+    if (((H | W) & 3) == 0 && L <= 2048) {
+        const int bw_n = W >> 2, nblk = (H >> 2) * bw_n;
+        for (int base = 0; base < nblk; base += 256) {
+            float4 rx[2][4], rg[2][4];
+            int h0[2], w0[2];
+            bool ok[2];
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                const int blk = base + it * 128 + tid;
+                ok[it] = blk < nblk;
+                const int bh = blk / bw_n, bw = blk - bh * bw_n;
+                h0[it] = bh << 2; w0[it] = bw << 2;
+                if (ok[it]) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        rx[it][i] = ldg128(x + (h0[it] + i) * W + w0[it]);
+                        rg[it][i] = ldg128(dy + (h0[it] + i) * W + w0[it]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+                if (ok[it]) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        *reinterpret_cast<float4*>(xN + swz_pos((h0[it] + i) * W + w0[it])) = rx[it][i];
+                        *reinterpret_cast<float4*>(gN + swz_pos((h0[it] + i) * W + w0[it])) = rg[it][i];
+                    }
+                    const int q = w0[it] * H + h0[it];
+                    *reinterpret_cast<float4*>(xT + swz_pos(q)) = make_float4(rx[it][0].x, rx[it][1].x, rx[it][2].x, rx[it][3].x);
+                    *reinterpret_cast<float4*>(xT + swz_pos(q + H)) = make_float4(rx[it][0].y, rx[it][1].y, rx[it][2].y, rx[it][3].y);
+                    *reinterpret_cast<float4*>(xT + swz_pos(q + 2 * H)) = make_float4(rx[it][0].z, rx[it][1].z, rx[it][2].z, rx[it][3].z);
+                    *reinterpret_cast<float4*>(xT + swz_pos(q + 3 * H)) = make_float4(rx[it][0].w, rx[it][1].w, rx[it][2].w, rx[it][3].w);
+                    *reinterpret_cast<float4*>(gT + swz_pos(q)) = make_float4(rg[it][0].x, rg[it][1].x, rg[it][2].x, rg[it][3].x);
+                    *reinterpret_cast<float4*>(gT + swz_pos(q + H)) = make_float4(rg[it][0].y, rg[it][1].y, rg[it][2].y, rg[it][3].y);
+                    *reinterpret_cast<float4*>(gT + swz_pos(q + 2 * H)) = make_float4(rg[it][0].z, rg[it][1].z, rg[it][2].z, rg[it][3].z);
+                    *reinterpret_cast<float4*>(gT + swz_pos(q + 3 * H)) = make_float4(rg[it][0].w, rg[it][1].w, rg[it][2].w, rg[it][3].w);
+                }
+            }
+        }
+        for (int q = L + tid; q < Lb; q += 128) {
+            const int sq = swz_pos(q);
+            xN[sq] = 0.0f; xT[sq] = 0.0f; gN[sq] = 0.0f; gT[sq] = 0.0f;
+        }
+    } else {
+        stage_image<float>(x, xN, xT, H, W, L, Lb, true, tid, 128);
+        stage_image<float>(dy, gN, gT, H, W, L, Lb, true, tid, 128);
+    }
 }
 
 struct LaneChunk {              // streamed operands of one chunk, as loaded (memory order)
@@ -127,10 +213,10 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
             // Granules outside the row (last chunk; the re-load after the final chunk) are read from a valid aligned offset
             // instead -- ONE unsigned min per granule covers both ends -- and callers neutralise what they hold.
             const unsigned o0 = min((unsigned)off, off_max), o1 = min((unsigned)(off + 4), off_max);
-            c.dt0 = ldg128(dt_row + o0); c.dt1 = ldg128(dt_row + o1);
-            c.B0 = ldg128(B_row + o0); c.B1 = ldg128(B_row + o1);
-            c.C0 = ldg128(C_row + o0); c.C1 = ldg128(C_row + o1);
-            c.hin = __ldg(st_row + min((unsigned)soff, soff_max));
+            c.dt0 = ldg128_pinned(dt_row + o0); c.dt1 = ldg128_pinned(dt_row + o1);
+            c.B0 = ldg128_pinned(B_row + o0); c.B1 = ldg128_pinned(B_row + o1);
+            c.C0 = ldg128_pinned(C_row + o0); c.C1 = ldg128_pinned(C_row + o1);
+            c.hin = ldg32_pinned(st_row + min((unsigned)soff, soff_max));
             off -= kChunk;
             soff += kRev ? 32 : -32;
         };
@@ -146,8 +232,7 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
         {
             const float* __restrict__ x = reinterpret_cast<const float*>(p.x) + ((int64_t)b * D + d) * L;
             const float* __restrict__ dyp = reinterpret_cast<const float*>(p.dy) + ((int64_t)b * D + d) * L;
-            stage_image<float>(x, xN, xT, H, W, L, Lb, true, tid, 128);
-            stage_image<float>(dyp, gN, gT, H, W, L, Lb, true, tid, 128);
+            stage_two_images(x, dyp, xN, xT, gN, gT, H, W, L, Lb, tid);
             cta_barrier();
         }
 
@@ -211,6 +296,7 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
             for (int i = 0; i < 4; ++i) dtB[i] = mul2(dt[i], Bv[i]);
             const int o = off + kChunk;            // this chunk's offset (`off` points at the next chunk until the re-load)
             load(c);
+            __syncwarp();                          // a barrier ptxas does not move the (coherent) loads across
             prefetch();
             if (kSoftplus && __any_sync(kFull, odd)) {
                 f2 Br[4];
@@ -283,8 +369,13 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
                     dthp[i] = mul2(dt[i], hp[i]);                               // dA += g dthp
                     dtu[i] = mul2(dt[i], u[i]);                                 // dB = g dtu
                 }
-                if (!(XFS_LANE_DIAG & 1) && st0) red_add_v4(dC_row + o, dCv[0].x, dCv[0].y, dCv[1].x, dCv[1].y);
-                if (!(XFS_LANE_DIAG & 1) && st1) red_add_v4(dC_row + o + 4, dCv[2].x, dCv[2].y, dCv[3].x, dCv[3].y);
+                if (!(XFS_LANE_DIAG & 1)) {
+                    if (!LAST) red_sector_pair<kRev ? -8 : 8>(dC_row, o, lane, dCv);
+                    else {
+                        if (st0) red_add_v4(dC_row + o, dCv[0].x, dCv[0].y, dCv[1].x, dCv[1].y);
+                        if (st1) red_add_v4(dC_row + o + 4, dCv[2].x, dCv[2].y, dCv[3].x, dCv[3].y);
+                    }
+                }
             }
             // ---- the adjoint across lanes: ONE warp scan per chunk, against the forward direction
             float q_out;
@@ -302,8 +393,13 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
             }
             if (!(XFS_LANE_DIAG & 2) && st0) stg128(ddt_row + o, dd[0], dd[1]);
             if (!(XFS_LANE_DIAG & 2) && st1) stg128(ddt_row + o + 4, dd[2], dd[3]);
-            if (!(XFS_LANE_DIAG & 1) && st0) red_add_v4(dB_row + o, dBv[0].x, dBv[0].y, dBv[1].x, dBv[1].y);
-            if (!(XFS_LANE_DIAG & 1) && st1) red_add_v4(dB_row + o + 4, dBv[2].x, dBv[2].y, dBv[3].x, dBv[3].y);
+            if (!(XFS_LANE_DIAG & 1)) {
+                if (!LAST) red_sector_pair<kRev ? -8 : 8>(dB_row, o, lane, dBv);
+                else {
+                    if (st0) red_add_v4(dB_row + o, dBv[0].x, dBv[0].y, dBv[1].x, dBv[1].y);
+                    if (st1) red_add_v4(dB_row + o + 4, dBv[2].x, dBv[2].y, dBv[3].x, dBv[3].y);
+                }
+            }
             // ---- du = D dy + g dt B into the pair's accumulator (position order: operands re-read with swapped halves)
             if (!LAST || in_buf_last) {
                 f2 gp[4], dtBp[4], du[4];
