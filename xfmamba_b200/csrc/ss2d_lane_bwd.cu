@@ -18,10 +18,15 @@ namespace xfs {
 using namespace ring;
 
 #ifndef XFS_LANE_DIAG
-#define XFS_LANE_DIAG 0          // timing experiments only: bit 0 = no dB / dC reductions, bit 1 = no ddelta stores
+#define XFS_LANE_DIAG 0          // timing experiments only (results wrong): bit 0 = no dB / dC reductions, 1 = no ddelta stores,
+                                 // 2 = no warp scan, 3 = MUFU replaced by FMA, 4 = no du accumulation, 5 = no walk at all
 #endif
 
 namespace {
+
+__device__ __forceinline__ float dex2(float x) { return (XFS_LANE_DIAG & 8) ? fmaf(x, 0.5f, 1.0f) : ex2(x); }
+__device__ __forceinline__ float dlg2(float x) { return (XFS_LANE_DIAG & 8) ? fmaf(x, 0.5f, -0.5f) : lg2(x); }
+__device__ __forceinline__ float drcp(float x) { return (XFS_LANE_DIAG & 8) ? fmaf(x, -0.25f, 1.0f) : rcp(x); }
 
 // All per-position arrays of the chunk loop are kept in MEMORY order (index 0 = lowest address of the lane's 8 elements
 // of a streamed row), as four packed pairs.  Rows are stored in scan order, so memory order IS the route's forward scan
@@ -53,6 +58,15 @@ __device__ __forceinline__ float ldg32_pinned(const float* p) {
     float v;
     asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
     return v;
+}
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256): a lane's 8 positions = one 32-byte sector = one instruction
+__device__ __forceinline__ void ldg256_pinned(const float* p, float4& a, float4& b) {
+    asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void stg256(float* p, f2 v0, f2 v1, f2 v2, f2 v3) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v0.x), "f"(v0.y), "f"(v1.x), "f"(v1.y),
+                 "f"(v2.x), "f"(v2.y), "f"(v3.x), "f"(v3.y) : "memory");
 }
 __device__ __forceinline__ void stg128(float* p, f2 lo, f2 hi) {
     asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(lo.x), "f"(lo.y), "f"(hi.x), "f"(hi.y) : "memory");
@@ -139,7 +153,8 @@ struct LaneChunk {              // streamed operands of one chunk, as loaded (me
 
 }  // namespace
 
-template <bool kSoftplus>
+// kV8: L % 8 == 0 and 32-byte aligned rows -- every lane's 8 positions are one aligned sector (256-bit loads and stores)
+template <bool kSoftplus, bool kV8>
 __global__ void __launch_bounds__(128, 3)
 ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
     extern __shared__ __align__(16) float smem[];
@@ -203,7 +218,7 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
         // 2/3 chunks 0 -> nch-1 (address = L-1 - position).  off = element offset of the granule at the lower address.
         int off = kRev ? L - 8 - 8 * lane : (nch - 1) * kChunk + 8 * lane;
         int soff = (kRev ? 0 : (nch - 1) * 32) + lane;     // checkpoint [j][lane] of the chunk being loaded
-        const unsigned off_max = (unsigned)(L - 4), soff_max = (unsigned)((nch - 1) * 32 + lane);
+        const unsigned off_max = (unsigned)(L - (kV8 ? 8 : 4)), soff_max = (unsigned)((nch - 1) * 32 + lane);
         // L2 prefetch ahead of the register loads: lanes 0-7 / 8-15 / 16-23 take the 128-byte lines of the dt / B / C chunk
         // rows (lanes 24-31 start so far below zero that their offset never turns non-negative)
         const float* pf_row = lane < 8 ? dt_row : (lane < 16 ? B_row : C_row);
@@ -213,9 +228,15 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
             // Granules outside the row (last chunk; the re-load after the final chunk) are read from a valid aligned offset
             // instead -- ONE unsigned min per granule covers both ends -- and callers neutralise what they hold.
             const unsigned o0 = min((unsigned)off, off_max), o1 = min((unsigned)(off + 4), off_max);
-            c.dt0 = ldg128_pinned(dt_row + o0); c.dt1 = ldg128_pinned(dt_row + o1);
-            c.B0 = ldg128_pinned(B_row + o0); c.B1 = ldg128_pinned(B_row + o1);
-            c.C0 = ldg128_pinned(C_row + o0); c.C1 = ldg128_pinned(C_row + o1);
+            if (kV8) {
+                ldg256_pinned(dt_row + o0, c.dt0, c.dt1);
+                ldg256_pinned(B_row + o0, c.B0, c.B1);
+                ldg256_pinned(C_row + o0, c.C0, c.C1);
+            } else {
+                c.dt0 = ldg128_pinned(dt_row + o0); c.dt1 = ldg128_pinned(dt_row + o1);
+                c.B0 = ldg128_pinned(B_row + o0); c.B1 = ldg128_pinned(B_row + o1);
+                c.C0 = ldg128_pinned(C_row + o0); c.C1 = ldg128_pinned(C_row + o1);
+            }
             c.hin = ldg32_pinned(st_row + min((unsigned)soff, soff_max));
             off -= kChunk;
             soff += kRev ? 32 : -32;
@@ -277,10 +298,10 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
             if (kSoftplus) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    e2[i] = make_float2(ex2(xl[i].x), ex2(xl[i].y));
+                    e2[i] = make_float2(dex2(xl[i].x), dex2(xl[i].y));
                     const f2 w = add2(e2[i], splat2(1.0f));
-                    dt[i] = mul2(make_float2(lg2(w.x), lg2(w.y)), splat2(kLn2));
-                    sig[i] = mul2(e2[i], make_float2(rcp(w.x), rcp(w.y)));     // sigmoid(x) = e / (1 + e)
+                    dt[i] = mul2(make_float2(dlg2(w.x), dlg2(w.y)), splat2(kLn2));
+                    sig[i] = mul2(e2[i], make_float2(drcp(w.x), drcp(w.y)));     // sigmoid(x) = e / (1 + e)
                 }
                 // chunk-uniform test: does any element need the small-argument series or the x > 20 identity?
                 odd = !(min8(e2) >= kEMin && max8(e2) <= kEMax);
@@ -300,7 +321,7 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
             prefetch();
             if (kSoftplus && __any_sync(kFull, odd)) {
                 f2 Br[4];
-                unpack(ldg128(B_row + min((unsigned)o, off_max)), ldg128(B_row + min((unsigned)(o + 4), off_max)), Br);
+                unpack(ldg128(B_row + min((unsigned)o, (unsigned)(L - 4))), ldg128(B_row + min((unsigned)(o + 4), (unsigned)(L - 4))), Br);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const f2 x = mul2(xl[i], splat2(kLn2)), e = e2[i];       // delta + bias again
@@ -333,7 +354,7 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const f2 ar = mul2(dt[i], splat2(A2));
-                    a[i] = make_float2(ex2(ar.x), ex2(ar.y));
+                    a[i] = make_float2(dex2(ar.x), dex2(ar.y));
                     bu[i] = mul2(dtB[i], u[i]);
                 }
                 float prev = hin;
@@ -379,7 +400,7 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
             }
             // ---- the adjoint across lanes: ONE warp scan per chunk, against the forward direction
             float q_out;
-            const float r_in = warp_prefix_p<!kRev>(Pl, Sl, qcarry, lane, q_out);
+            const float r_in = (XFS_LANE_DIAG & 4) ? (q_out = fmaf(Pl, qcarry, Sl), qcarry) : warp_prefix_p<!kRev>(Pl, Sl, qcarry, lane, q_out);
             qcarry = q_out;
 
             f2 g[4], dd[4], dBv[4];
@@ -391,8 +412,12 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
                 dA2 = fma2(g[i], dthp[i], dA2);
                 dbias2 = add2(dbias2, dd[i]);          // dt = 0 beyond L makes these terms exactly 0 (h_prev = 0 or g = 0 there)
             }
-            if (!(XFS_LANE_DIAG & 2) && st0) stg128(ddt_row + o, dd[0], dd[1]);
-            if (!(XFS_LANE_DIAG & 2) && st1) stg128(ddt_row + o + 4, dd[2], dd[3]);
+            if (kV8) {
+                if (!(XFS_LANE_DIAG & 2) && st0) stg256(ddt_row + o, dd[0], dd[1], dd[2], dd[3]);
+            } else {
+                if (!(XFS_LANE_DIAG & 2) && st0) stg128(ddt_row + o, dd[0], dd[1]);
+                if (!(XFS_LANE_DIAG & 2) && st1) stg128(ddt_row + o + 4, dd[2], dd[3]);
+            }
             if (!(XFS_LANE_DIAG & 1)) {
                 if (!LAST) red_sector_pair<kRev ? -8 : 8>(dB_row, o, lane, dBv);
                 else {
@@ -401,7 +426,8 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
                 }
             }
             // ---- du = D dy + g dt B into the pair's accumulator (position order: operands re-read with swapped halves)
-            if (!LAST || in_buf_last) {
+            if (XFS_LANE_DIAG & 16) { dA2 = fma2(g[0], dtB[1], dA2); }
+            else if (!LAST || in_buf_last) {
                 f2 gp[4], dtBp[4], du[4];
                 reorder<kRev>(g, gp);
                 reorder<kRev>(dtB, dtBp);
@@ -416,7 +442,8 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
 
         const std::true_type T{};
         const std::false_type F{};
-        if (!kRev) {                   // chunks nch-1 -> 0; first touches [m, nch)
+        if (XFS_LANE_DIAG & 32) { pair_barrier(k & 1); }
+        else if (!kRev) {                   // chunks nch-1 -> 0; first touches [m, nch)
             uint32_t ib = (uint32_t)(nch - 1) * (kChunk * 4);
             chunk(ib, T, T);
             int j = nch - 2;
@@ -467,13 +494,17 @@ int launch_ss2d_lane_bwd(const xfs_ss2d_bwd_args& a, cudaStream_t st) {
         return XFS_ERR_ALIGN;
     const size_t smem = bwd_smem(a.H * a.W, 1, 1);
     const unsigned grid = (unsigned)(a.batch * a.D);
-    if (a.delta_softplus) {
-        if (int rc = set_smem(ss2d_lane_bwd_kernel<true>, smem)) return rc;
-        ss2d_lane_bwd_kernel<true><<<grid, 128, smem, st>>>(a);
-    } else {
-        if (int rc = set_smem(ss2d_lane_bwd_kernel<false>, smem)) return rc;
-        ss2d_lane_bwd_kernel<false><<<grid, 128, smem, st>>>(a);
-    }
+    auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
+    const bool v8 = (a.H * a.W) % 8 == 0 && al32(a.delta) && al32(a.Bs) && al32(a.Cs) && al32(a.ddelta);
+    auto go = [&](auto kern) -> int {
+        if (int rc = set_smem(kern, smem)) return rc;
+        kern<<<grid, 128, smem, st>>>(a);
+        return 0;
+    };
+    int rc;
+    if (a.delta_softplus) rc = v8 ? go(ss2d_lane_bwd_kernel<true, true>) : go(ss2d_lane_bwd_kernel<true, false>);
+    else rc = v8 ? go(ss2d_lane_bwd_kernel<false, true>) : go(ss2d_lane_bwd_kernel<false, false>);
+    if (rc) return rc;
     return check_launch();
 }
 
