@@ -69,6 +69,23 @@ def test_scalars_and_error_strings(L):
     assert L.xfs_launch_count() >= 0
 
 
+def test_ss2d_checkpoint_row_length(L):
+    """xfs_ss2d_states_len: floats per (batch, 4*D) row of the checkpoints the fused forward writes.  One state per chunk
+    and n in general; one per LANE and chunk (32 per chunk) on the backbone path (f32, N == 1, L % 4 == 0, L > 256,
+    working set within shared memory), whose backward replays 8 positions per lane from them."""
+    F32, BF16 = 0, 1
+    f = L.xfs_ss2d_states_len
+    assert f(1, 56, 56, F32, F32) == 13 * 32            # config 2: lane checkpoints
+    assert f(1, 28, 28, F32, F32) == 4 * 32
+    assert f(1, 56, 56, BF16, F32) == 13                # 16-bit rows: chunk checkpoints
+    assert f(16, 56, 56, F32, F32) == 13 * 16           # N > 1
+    assert f(1, 14, 14, F32, F32) == 1                  # one chunk
+    assert f(1, 7, 7, F32, F32) == 1
+    assert f(1, 57, 57, F32, F32) == 13                 # L % 4 != 0: generic kernels
+    assert f(1, 128, 128, F32, F32) == 64               # beyond the fused working set: chunk checkpoints (stand-alone scan)
+    assert f(0, 1, 1, F32, F32) == 0
+
+
 def test_argument_errors_are_negative_codes(L):
     from xfmamba_b200 import _lib
     vp = ctypes.c_void_p

@@ -42,7 +42,9 @@ for r in rows[2:]:
     d = dict(zip(hdr, r))
     u = dict(zip(hdr, units))
     name = d["Kernel Name"]
-    short = "ss2d_fwd_kernel" if "ss2d_fwd" in name else "ss2d_bwd_kernel" if "ss2d_bwd" in name else name.split("(")[0]
+    import re as _re
+    _m = _re.search(r"(\w+_kernel)", name)
+    short = _m.group(1) if _m else name.split("(")[0]
     def g(k):
         return float(d[k]) if d.get(k) not in (None, "") else float("nan")
     scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}

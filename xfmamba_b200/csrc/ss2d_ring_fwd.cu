@@ -238,7 +238,7 @@ ss2d_ring_fwd_kernel(const xfs_ss2d_fwd_args p) {
 
         float h_out, h_in;
         if (kDiag & 4) { h_in = carry; h_out = fmaf(PA * PB, carry, o.a_first ? fmaf(PB, SA, SB) : fmaf(PA, SB, SA)); }
-        else h_in = warp_prefix<R>(PA * PB, o.a_first ? fmaf(PB, SA, SB) : fmaf(PA, SB, SA), carry, lane, h_out);
+        else h_in = warp_prefix_p<R>(PA * PB, o.a_first ? fmaf(PB, SA, SB) : fmaf(PA, SB, SA), carry, lane, h_out);
         carry = h_out;
         if (st_ptr) {
             *st_ptr = h_in;
