@@ -251,7 +251,7 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
         };
         auto prefetch = [&]() __attribute__((always_inline)) {
             pf_off -= kChunk;
-            if (pf_off >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_row + pf_off));
+            if (!(XFS_LANE_DIAG & 64) && pf_off >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_row + pf_off));
         };
 
         LaneChunk c;
