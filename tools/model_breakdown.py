@@ -22,5 +22,5 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
 ev = prof.key_averages()
 tot = sum(e.device_time_total for e in ev)
 print(f"{variant} batch {batch} {'train' if train else 'infer'} {'bf16' if amp else 'fp32'}: total device time {tot/1e3:.2f} ms")
-for e in sorted(ev, key=lambda e: -e.device_time_total)[:14]:
+for e in sorted(ev, key=lambda e: -e.device_time_total)[:45]:
     print(f"  {100*e.device_time_total/tot:5.1f}%  {e.device_time_total/1e3:8.2f} ms  x{e.count:<5} {e.key[:90]}")
