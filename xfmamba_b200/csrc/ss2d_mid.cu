@@ -258,91 +258,157 @@ ss2d_mid_fwd_kernel(const xfs_ss2d_fwd_args p) {
 
 // ---- one route of the backward ------------------------------------------------------------------------------------------
 // u, dy: this route's position order (row-major for routes 0/2, column-major for 1/3); du accumulates in the same order.
+// Arithmetic as in ss2d_lane_bwd.cu: everything per position is kept in MEMORY order (= the forward scan order of every
+// route: the rows are stored in scan order), so the folds run over ascending / descending indices for all four routes and
+// ddelta / dB / dC come out in store order; the register-held u / dy of a flipped route are read with swapped halves.  One
+// chunk, no checkpoints: the forward fold and the adjoint fold share one interleaved pair of warp scans (predicates from
+// shfl.sync), softplus takes the fast lg2(1 + e) form and repairs outliers under one warp vote.
+__device__ __forceinline__ f2 mid_swp(const f2 v) { return make_float2(v.y, v.x); }
+template <bool kRev>
+__device__ __forceinline__ void mid_reorder(const f2 (&v)[4], f2 (&o)[4]) {      // position order <-> memory order
+#pragma unroll
+    for (int q = 0; q < 4; ++q) o[q] = kRev ? mid_swp(v[3 - q]) : v[q];
+}
+__device__ __forceinline__ float& mid_el(f2 (&v)[4], int i) { return (i & 1) ? v[i >> 1].y : v[i >> 1].x; }
+
+// forward fold (P, S) scanned along the forward direction (lanes ascending unless kRev), adjoint (Pq, Sq) against it; both
+// start from 0 (one chunk).  Returns the state entering each lane for both.
+template <bool kRev>
+__device__ __forceinline__ void mid_scan_pair(float P, float S, float Pq, float Sq, float& h_in, float& r_in) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+#define XFS_SCAN_STEP(DIR, CL, PP, SS)                                                                              \
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .f32 pn, sn;\n\t"                                                 \
+                     "shfl.sync." DIR ".b32 pn|p, %0, %2, " CL ", 0xffffffff;\n\t"                                  \
+                     "shfl.sync." DIR ".b32 sn, %1, %2, " CL ", 0xffffffff;\n\t"                                    \
+                     "@p fma.rn.ftz.f32 %1, %0, sn, %1;\n\t"                                                       \
+                     "@p mul.ftz.f32 %0, %0, pn;\n\t}"                                                             \
+                     : "+f"(PP), "+f"(SS) : "r"(off))
+        if (kRev) { XFS_SCAN_STEP("down", "0x1f", P, S); XFS_SCAN_STEP("up", "0", Pq, Sq); }
+        else { XFS_SCAN_STEP("up", "0", P, S); XFS_SCAN_STEP("down", "0x1f", Pq, Sq); }
+#undef XFS_SCAN_STEP
+    }
+    h_in = 0.0f; r_in = 0.0f;
+#define XFS_SCAN_PREV(DIR, CL, OUT, IN)                                                                             \
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .f32 t;\n\tshfl.sync." DIR ".b32 t|p, %1, 1, " CL ", 0xffffffff;\n\t@p mov.f32 %0, t;\n\t}" \
+                 : "+f"(OUT) : "f"(IN))
+    if (kRev) { XFS_SCAN_PREV("down", "0x1f", h_in, S); XFS_SCAN_PREV("up", "0", r_in, Sq); }
+    else { XFS_SCAN_PREV("up", "0", h_in, S); XFS_SCAN_PREV("down", "0x1f", r_in, Sq); }
+#undef XFS_SCAN_PREV
+}
+
 template <bool kRev, typename T>
 __device__ __forceinline__ void mid_route_bwd(const xfs_ss2d_bwd_args& p, const MidLoads& r, T* __restrict__ ddt_row,
                                               float* __restrict__ dBrow, float* __restrict__ dCrow, const MidLane& m, int L, int lane,
                                               const float (&u)[8], const float (&dy)[8], float (&du)[8], float (&pg)[3]) {
     const int g0 = kRev ? m.g0r : m.g0f, g1 = kRev ? m.g1r : m.g1f;
     const float bias = r.bias, Dd = r.Dd, An = r.A, A2 = An * kLog2e;
-    const float (&dta)[8] = r.dt;
-    const float (&Ba)[8] = r.B;
-    const float (&Ca)[8] = r.C;
-    float dtp[8], Bp[8], Cp[8];
-    to_pos<kRev>(dta, dtp); to_pos<kRev>(Ba, Bp); to_pos<kRev>(Ca, Cp);
-    const float off = p.delta_softplus ? -INFINITY : -bias;      // positions >= L: dt = 0 makes every term below exactly 0
+    // memory order: streamed rows as loaded; u / dy (position order in registers) re-read with swapped halves when flipped
+    f2 xr[4], Bv[4], Cv[4], up[4], dyp[4], um[4], dym[4];
+    pack8(r.dt, xr); pack8(r.B, Bv); pack8(r.C, Cv); pack8(u, up); pack8(dy, dyp);
+    mid_reorder<kRev>(up, um);
+    mid_reorder<kRev>(dyp, dym);
+    f2 dt[4], sig[4], e2[4];
+    if (p.delta_softplus) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-        if (m.p0 + i >= L) dtp[i] = off;
-    f2 x2[4], u2[4], dy2[4], B2[4], C2[4], dt2[4], sig2[4], a2[4], bu2[4], Bu2[4], cd2[4];
-    pack8(dtp, x2); pack8(u, u2); pack8(dy, dy2); pack8(Bp, B2); pack8(Cp, C2);
-    f2 dD2 = splat2(0.0f);
+        for (int i = 0; i < 4; ++i) {
+            const f2 xl = fma2(xr[i], splat2(kLog2e), splat2(bias * kLog2e));
+            e2[i] = ex2_2(xl);
+            const f2 w = add2(e2[i], splat2(1.0f));
+            dt[i] = mul2(make_float2(lg2(w.x), lg2(w.y)), splat2(kLn2));
+            sig[i] = mul2(e2[i], make_float2(rcp(w.x), rcp(w.y)));      // sigmoid(x) = e / (1 + e)
+        }
+        const float emin = fminf(fminf(fminf(e2[0].x, e2[0].y), fminf(e2[1].x, e2[1].y)), fminf(fminf(e2[2].x, e2[2].y), fminf(e2[3].x, e2[3].y)));
+        const float emax = fmaxf(fmaxf(fmaxf(e2[0].x, e2[0].y), fmaxf(e2[1].x, e2[1].y)), fmaxf(fmaxf(e2[2].x, e2[2].y), fmaxf(e2[3].x, e2[3].y)));
+        // does any element need the small-argument series (e < 2^-6) or the x > 20 identity?  (see softplus_fwd)
+        if (__any_sync(kFull, !(emin >= 0.015625f && emax <= 268435456.0f))) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const f2 xx = add2(x2[j], splat2(bias));
-        f2 e = splat2(0.0f);
-        dt2[j] = p.delta_softplus ? softplus2(xx, e) : xx;
-        const f2 w = add2(e, splat2(1.0f));
-        f2 sg = mul2(e, make_float2(rcp(w.x), rcp(w.y)));       // sigmoid(x) = e / (1 + e); x > 20: softplus is the identity
-        sg.x = (xx.x > 20.0f) ? 1.0f : sg.x;
-        sg.y = (xx.y > 20.0f) ? 1.0f : sg.y;
-        sig2[j] = p.delta_softplus ? sg : splat2(1.0f);
-        Bu2[j] = mul2(B2[j], u2[j]);
-        cd2[j] = mul2(C2[j], dy2[j]);
-        a2[j] = ex2_2(mul2(dt2[j], splat2(A2)));
-        bu2[j] = mul2(dt2[j], Bu2[j]);
-        dD2 = fma2(dy2[j], u2[j], dD2);
+            for (int i = 0; i < 4; ++i) {
+                const f2 x = add2(xr[i], splat2(bias)), e = e2[i];
+                f2 ser = fma2(e, splat2(-0.25f), splat2(0.33333334f));
+                ser = fma2(ser, e, splat2(-0.5f));
+                ser = fma2(ser, e, splat2(1.0f));
+                ser = mul2(ser, e);
+                f2 q;
+                q.x = (e.x < 0.015625f) ? ser.x : dt[i].x;
+                q.y = (e.y < 0.015625f) ? ser.y : dt[i].y;
+                dt[i].x = (x.x > 20.0f) ? x.x : q.x;
+                dt[i].y = (x.y > 20.0f) ? x.y : q.y;
+                sig[i].x = (x.x > 20.0f) ? 1.0f : sig[i].x;
+                sig[i].y = (x.y > 20.0f) ? 1.0f : sig[i].y;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { dt[i] = add2(xr[i], splat2(bias)); sig[i] = splat2(1.0f); }
     }
-    float a[8], bu[8], cd[8], S[8], P[8], Sq[8], Pq[8];
-    unpack8(a2, a); unpack8(bu2, bu); unpack8(cd2, cd);
-    float Pr = 1.0f, Sr = 0.0f, Pqr = 1.0f, Sqr = 0.0f;
+    // positions >= L: identity maps (dt = 0); validity of the low / high ADDRESS granule
+    const bool okA = kRev ? m.ok1 : m.ok0, okB = kRev ? m.ok0 : m.ok1;
+    if (!okA) { dt[0] = dt[1] = splat2(0.0f); }
+    if (!okB) { dt[2] = dt[3] = splat2(0.0f); }
+    if ((L & 3) != 0) {}                                   // (L % 4 == 0 here: granules are entirely inside or outside)
+
+    f2 a[4], bu[4], Bu[4], cd[4], dtB[4];
 #pragma unroll
-    for (int ii = 0; ii < 8; ++ii) {           // forward re-scan, walk order
-        const int i = kRev ? 7 - ii : ii;
-        Sr = fmaf(a[i], Sr, bu[i]); Pr *= a[i]; S[i] = Sr; P[i] = Pr;
+    for (int i = 0; i < 4; ++i) {
+        a[i] = ex2_2(mul2(dt[i], splat2(A2)));
+        Bu[i] = mul2(Bv[i], um[i]);
+        dtB[i] = mul2(dt[i], Bv[i]);
+        bu[i] = mul2(dt[i], Bu[i]);
+        cd[i] = mul2(Cv[i], dym[i]);
     }
+    // forward fold over ascending memory indices, adjoint fold over descending ones
+    f2 S[4], P[4], G[4], Pq[4];
+    float Sr = 0.0f, Pr = 1.0f;
 #pragma unroll
-    for (int ii = 0; ii < 8; ++ii) {           // adjoint scan, opposite order
-        const int i = kRev ? ii : 7 - ii;
-        Sqr = a[i] * (cd[i] + Sqr); Pqr *= a[i]; Sq[i] = Sqr; Pq[i] = Pqr;
+    for (int i = 0; i < 8; ++i) {
+        Sr = fmaf(mid_el(a, i), Sr, mid_el(bu, i));
+        Pr = (i == 0) ? mid_el(a, 0) : Pr * mid_el(a, i);
+        mid_el(S, i) = Sr; mid_el(P, i) = Pr;
     }
-    float h_in, q_in, q_out;
-    warp_prefix_dual<kRev>(Pr, Sr, 0.0f, Pqr, Sqr, 0.0f, lane, h_in, q_in, q_out);
-    float q[8], gi[8];
+    float Gp = mid_el(cd, 7), Pp = 1.0f;
+    mid_el(G, 7) = Gp; mid_el(Pq, 7) = 1.0f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) q[i] = fmaf(Pq[i], q_in, Sq[i]);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {              // g_i = C_i dy_i + q of the element that FOLLOWS i in the forward walk
-        const float qn = kRev ? (i == 0 ? q_in : q[i == 0 ? 0 : i - 1]) : (i == 7 ? q_in : q[i == 7 ? 7 : i + 1]);
-        gi[i] = cd[i] + qn;
+    for (int i = 6; i >= 0; --i) {
+        const float an = mid_el(a, i + 1);
+        Gp = fmaf(an, Gp, mid_el(cd, i));
+        Pp = (i == 6) ? an : Pp * an;
+        mid_el(G, i) = Gp; mid_el(Pq, i) = Pp;
     }
-    f2 S2[4], P2[4], gi2[4], dB2[4], dC2[4], ddt2[4];
-    pack8(S, S2); pack8(P, P2); pack8(gi, gi2);
-    f2 dA2 = splat2(0.0f), dbias2 = splat2(0.0f);
+    float h_in, r_in;
+    mid_scan_pair<kRev>(Pr, Sr, mid_el(a, 0) * Pp, mid_el(a, 0) * Gp, h_in, r_in);
+
+    f2 dD2 = splat2(0.0f), dA2 = splat2(0.0f), dbias2 = splat2(0.0f), g[4], dd[4], dBv[4], dCv[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const f2 h2 = fma2(P2[j], splat2(h_in), S2[j]);
-        const f2 hp2 = fma2(bu2[j], splat2(-1.0f), h2);         // a_i * h_{i-1}
-        const f2 gdt2 = mul2(gi2[j], dt2[j]);
-        const f2 du2 = fma2(gdt2, B2[j], mul2(splat2(Dd), dy2[j]));
-        du[2 * j] += du2.x; du[2 * j + 1] += du2.y;
-        ddt2[j] = mul2(mul2(gi2[j], fma2(splat2(An), hp2, Bu2[j])), sig2[j]);
-        dbias2 = add2(dbias2, ddt2[j]);
-        dA2 = fma2(gdt2, hp2, dA2);
-        dB2[j] = mul2(gdt2, u2[j]);
-        dC2[j] = mul2(dy2[j], h2);
+    for (int i = 0; i < 4; ++i) {
+        const f2 h = fma2(P[i], splat2(h_in), S[i]);
+        const f2 hp = fma2(bu[i], splat2(-1.0f), h);                 // a_i h_prev
+        g[i] = fma2(Pq[i], splat2(r_in), G[i]);
+        const f2 gdt = mul2(g[i], dt[i]);
+        dd[i] = mul2(mul2(g[i], fma2(splat2(An), hp, Bu[i])), sig[i]);
+        dA2 = fma2(gdt, hp, dA2);
+        dBv[i] = mul2(gdt, um[i]);
+        dCv[i] = mul2(dym[i], h);
+        dD2 = fma2(dym[i], um[i], dD2);
+        dbias2 = add2(dbias2, dd[i]);
     }
-    // ddelta, dB, dC back in address order of this route's rows
-    float v[8], va[8];
-    unpack8(ddt2, v); to_pos<kRev>(v, va);
-    const bool okA = kRev ? m.ok1 : m.ok0, okB = kRev ? m.ok0 : m.ok1;      // validity of the low / high ADDRESS granule
-    if (okA) mid_store4<T>(ddt_row + g0, va[0], va[1], va[2], va[3]);
-    if (okB) mid_store4<T>(ddt_row + g1, va[4], va[5], va[6], va[7]);
-    unpack8(dB2, v); to_pos<kRev>(v, va);
-    if (okA) red_add_v4_relaxed(dBrow + g0, va[0], va[1], va[2], va[3]);
-    if (okB) red_add_v4_relaxed(dBrow + g1, va[4], va[5], va[6], va[7]);
-    unpack8(dC2, v); to_pos<kRev>(v, va);
-    if (okA) red_add_v4_relaxed(dCrow + g0, va[0], va[1], va[2], va[3]);
-    if (okB) red_add_v4_relaxed(dCrow + g1, va[4], va[5], va[6], va[7]);
+    // du in position order: operands re-read with swapped halves
+    {
+        f2 gp[4], dtBp[4];
+        mid_reorder<kRev>(g, gp);
+        mid_reorder<kRev>(dtB, dtBp);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const f2 d2 = fma2(gp[i], dtBp[i], mul2(splat2(Dd), dyp[i]));
+            du[2 * i] += d2.x; du[2 * i + 1] += d2.y;
+        }
+    }
+    if (okA) mid_store4<T>(ddt_row + g0, dd[0].x, dd[0].y, dd[1].x, dd[1].y);
+    if (okB) mid_store4<T>(ddt_row + g1, dd[2].x, dd[2].y, dd[3].x, dd[3].y);
+    if (okA) red_add_v4_relaxed(dBrow + g0, dBv[0].x, dBv[0].y, dBv[1].x, dBv[1].y);
+    if (okB) red_add_v4_relaxed(dBrow + g1, dBv[2].x, dBv[2].y, dBv[3].x, dBv[3].y);
+    if (okA) red_add_v4_relaxed(dCrow + g0, dCv[0].x, dCv[0].y, dCv[1].x, dCv[1].y);
+    if (okB) red_add_v4_relaxed(dCrow + g1, dCv[2].x, dCv[2].y, dCv[3].x, dCv[3].y);
     // parameter gradients of this (route, channel): per-lane partial sums, reduced and added once at the end of the kernel
     pg[0] = dA2.x + dA2.y; pg[1] = dD2.x + dD2.y; pg[2] = dbias2.x + dbias2.y;
 }
