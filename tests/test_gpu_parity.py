@@ -382,6 +382,28 @@ def test_ss2d_full_size_properties(xf):
     assert rel_err(n(y_rot), n(yf.flip(2))) < TOL32
 
 
+@pytest.mark.parametrize("shape", [(1, 3, 1, 20, 24), (2, 2, 1, 13, 20), (1, 4, 1, 14, 14)])
+def test_ss2d_softplus_outliers_vs_oracle(xf, shape):
+    """softplus regimes the fast lg2(1 + e) form does not cover, mixed inside single chunks: delta + bias far below zero (the
+    e < 2^-6 series; models/csms6s.py:49-50 computes log1p(exp(x))), above the threshold 20 (identity, sigmoid = 1) and
+    ordinary values -- the multi-chunk lane-checkpoint kernels (L = 480, 260: 256-bit and 128-bit rows) and the one-chunk
+    kernel repair those under a warp vote, the backward after re-reading B."""
+    Bsz, D, N, H, W = shape
+    L = H * W
+    rng = np.random.default_rng(abs(hash(shape)) % 2**32)
+    c = _rand_ss2d(rng, Bsz, D, N, H, W)
+    pick = rng.integers(0, 4, size=c["delta"].shape)
+    c["delta"] = np.where(pick == 0, -12.0 + 2.0 * rng.random(c["delta"].shape),
+                          np.where(pick == 1, 20.5 + 3.0 * rng.random(c["delta"].shape), c["delta"])).astype(np.float32)
+    c["A"] = (0.02 * c["A"]).astype(np.float32)                       # keep exp(dt A) away from underflow at dt ~ 23
+    y, leaves = _run_ss2d(xf, c)
+    ref = oracle.ss2d_fwd(c["x"], c["delta"], c["A"], c["Bs"], c["Cs"], c["Ds"], c["delta_bias"], True, "f64")
+    assert rel_err(n(y), ref) < TOL32
+    grads = oracle.ss2d_bwd(c["x"], c["delta"], c["A"], c["Bs"], c["Cs"], c["Ds"], c["delta_bias"], c["dy"], True, "f64")
+    for k, gr in zip(SS2D_KEYS, grads):
+        assert rel_err(n(leaves[k].grad), gr) < TOL32, f"d{k}"
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_ss2d_config2_shape_vs_oracle(xf, dtype):
     """BASELINE config 2 at its exact per-image shape (D = 192, 56x56, N = 1, K = 4; 8 images) against the CPU oracle:
