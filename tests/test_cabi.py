@@ -77,7 +77,9 @@ def test_ss2d_checkpoint_row_length(L):
     f = L.xfs_ss2d_states_len
     assert f(1, 56, 56, F32, F32) == 13 * 32            # config 2: lane checkpoints
     assert f(1, 28, 28, F32, F32) == 4 * 32
-    assert f(1, 56, 56, BF16, F32) == 13                # 16-bit rows: chunk checkpoints
+    assert f(1, 56, 56, BF16, F32) == 13 * 32           # 16-bit rows, fp32 output, L % 8 == 0: lane checkpoints too
+    assert f(1, 56, 56, BF16, BF16) == 13               # 16-bit output: chunk checkpoints (generic kernels)
+    assert f(1, 18, 18, BF16, F32) == 2                 # L % 8 != 0
     assert f(16, 56, 56, F32, F32) == 13 * 16           # N > 1
     assert f(1, 14, 14, F32, F32) == 1                  # one chunk
     assert f(1, 7, 7, F32, F32) == 1

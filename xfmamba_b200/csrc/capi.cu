@@ -12,6 +12,7 @@ int launch_swap(const void*, const void*, void*, void*, int64_t, int64_t, int64_
 int launch_scan_fwd(const xfs_scan_fwd_args&, cudaStream_t);
 int launch_scan_bwd(const xfs_scan_bwd_args&, cudaStream_t);
 int launch_ss2d_fwd(const xfs_ss2d_fwd_args&, cudaStream_t);
+int launch_ss2d_fwd_lane16(const xfs_ss2d_fwd_args&, cudaStream_t);
 int launch_ss2d_bwd(const xfs_ss2d_bwd_args&, cudaStream_t);
 int ss2d_supported(int64_t, int64_t, int64_t, int64_t, int, int);
 int ss2d_small_supported(int64_t, int64_t, int64_t);
@@ -169,7 +170,8 @@ int xfs_ss2d_fwd(const xfs_ss2d_fwd_args* a, xfs_stream_t stream) {
     // ss2d_lane_bwd.cu reads: with checkpoints requested it runs exactly when that backward will.
     const bool lane_states = ss2d_lane_states(a->N, a->H, a->W, a->dtype, a->out_dtype);
     if (ss2d_ring_fwd_supported(*a) && (a->states == nullptr || lane_states)) return launch_ss2d_ring_fwd(*a, (cudaStream_t)stream);
-    if (a->states != nullptr && lane_states) return XFS_ERR_ALIGN;      // shape of the lane-checkpoint path, misaligned rows
+    if (a->states != nullptr && lane_states)       // lane-checkpoint path: 16-bit rows take the register-fed kernel; fp32 rows get here only when misaligned
+        return a->dtype == XFS_F32 ? XFS_ERR_ALIGN : launch_ss2d_fwd_lane16(*a, (cudaStream_t)stream);
     if (!ss2d_supported(a->D, a->N, a->H, a->W, a->dtype, 0)) return XFS_ERR_UNSUPPORTED;
     return launch_ss2d_fwd(*a, (cudaStream_t)stream);
 }

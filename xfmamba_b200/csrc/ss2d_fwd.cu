@@ -12,7 +12,9 @@ struct FwdChunk {            // delta/B/C of one chunk of one route, in ADDRESS 
 // kN == 1: single state carried in a register; kN == 0: runtime N (<= kFusedMaxState), states carried in smem
 // kSingle: the sequence fits ONE chunk (L <= 256) -> no chunk loop, no carried state; the leaner code needs fewer
 // registers, so more CTAs fit per SM (these short shapes -- XFMamba's 14x14 stage has 15 of the 21 blocks -- are latency bound)
-template <typename T, typename TO, int kN, int kCh, bool kFast, bool kSingle>
+// kLane: LANE-granular checkpoints for ss2d_lane_bwd.cu (16-bit rows; fp32 rows get them from ss2d_ring_fwd.cu): row (b, k*D+d)
+// holds nch x 32 floats, entry [j][lane] = the state entering the 8 positions of lane `lane` of position-order chunk j
+template <typename T, typename TO, int kN, int kCh, bool kFast, bool kSingle, bool kLane = false>
 __global__ void __launch_bounds__(128, kSingle ? 6 : 4)
 ss2d_fwd_kernel(const xfs_ss2d_fwd_args p) {
     extern __shared__ __align__(16) float smem[];
@@ -52,7 +54,7 @@ ss2d_fwd_kernel(const xfs_ss2d_fwd_args p) {
     for (int ch = 0; ch < kCh; ++ch) {
         kd[ch] = k * D + (valid[ch] ? d0 + ch : d0);
         dt_row[ch] = delta + ((int64_t)b * 4 * D + kd[ch]) * L;
-        st_row[ch] = (p.states && valid[ch]) ? p.states + ((int64_t)b * 4 * D + kd[ch]) * nch * N : nullptr;
+        st_row[ch] = (p.states && valid[ch]) ? p.states + ((int64_t)b * 4 * D + kd[ch]) * nch * (kLane ? 32 : N) : nullptr;
         bias[ch] = p.delta_bias ? p.delta_bias[kd[ch]] : 0.0f;
         Dd[ch] = p.Ds ? p.Ds[kd[ch]] : 0.0f;
         A2_1[ch] = (kN == 1) ? p.A[kd[ch]] * kLog2e : 0.0f;
@@ -231,7 +233,8 @@ ss2d_fwd_kernel(const xfs_ss2d_fwd_args p) {
                     for (int jj = 0; jj < 4; ++jj) y2[ch][jj] = fma2(C2[jj], fma2(P2[jj], hin2, S2[jj]), y2[ch][jj]);
                     if (kN == 1) carry1[ch] = h_out;
                     else { __syncwarp(); if (lane == 0) *hs = h_out; }
-                    if (st_row[ch] && lane == 0) st_row[ch][j * N + n] = h_out;
+                    if (kLane) { if (st_row[ch]) st_row[ch][j * 32 + lane] = h_in; }
+                    else if (st_row[ch] && lane == 0) st_row[ch][j * N + n] = h_out;
                 }
             }
             // ---- accumulate into the pair's buffer
@@ -304,6 +307,19 @@ static int launch_fwd_tt(const xfs_ss2d_fwd_args& a, cudaStream_t st) {
         if (fast) return a.N == 1 ? launch_fwd_k<T, TO, 1, true>(a, st) : launch_fwd_k<T, TO, 0, true>(a, st);
     }
     return a.N == 1 ? launch_fwd_k<T, TO, 1, false>(a, st) : launch_fwd_k<T, TO, 0, false>(a, st);
+}
+
+// 16-bit rows, fp32 output, N == 1, L % 8 == 0, more than one chunk: the fast kernel with lane-granular checkpoints
+template <typename T>
+static int launch_fwd_lane_t(const xfs_ss2d_fwd_args& a, cudaStream_t st) {
+    const size_t smem = fwd_smem(a.H * a.W, 1, kChFwd);
+    if (int rc = set_smem(ss2d_fwd_kernel<T, float, 1, kChFwd, true, false, true>, smem)) return rc;
+    ss2d_fwd_kernel<T, float, 1, kChFwd, true, false, true><<<(unsigned)(a.batch * a.D), 128, smem, st>>>(a);
+    return check_launch();
+}
+int launch_ss2d_fwd_lane16(const xfs_ss2d_fwd_args& a, cudaStream_t st) {
+    if (!(aligned16(a.x) && aligned16(a.delta) && aligned16(a.Bs) && aligned16(a.Cs) && aligned16(a.y))) return XFS_ERR_ALIGN;
+    return a.dtype == XFS_BF16 ? launch_fwd_lane_t<__nv_bfloat16>(a, st) : launch_fwd_lane_t<__half>(a, st);
 }
 
 int launch_ss2d_fwd(const xfs_ss2d_fwd_args& a, cudaStream_t st) {

@@ -146,15 +146,69 @@ __device__ __forceinline__ void stage_two_images(const float* __restrict__ x, co
     }
 }
 
+// ---- streamed rows by element type.  fp32: two 16-byte granules per lane (or one 256-bit access, kV8); bf16 / f16: the lane's 8
+// positions are ONE 16-byte granule (L % 8 == 0), kept as raw bits until they are consumed at the top of the next chunk.
+template <typename T> struct RowRaw { float4 g0, g1; };
+template <> struct RowRaw<__nv_bfloat16> { uint4 g; };
+template <> struct RowRaw<__half> { uint4 g; };
+
+__device__ __forceinline__ uint4 ldg128u_pinned(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+template <bool kV8>
+__device__ __forceinline__ void row_load(RowRaw<float>& r, const float* row, unsigned o0, unsigned o1) {
+    if (kV8) ldg256_pinned(row + o0, r.g0, r.g1);
+    else { r.g0 = ldg128_pinned(row + o0); r.g1 = ldg128_pinned(row + o1); }
+}
+template <bool kV8, typename T>
+__device__ __forceinline__ void row_load(RowRaw<T>& r, const T* row, unsigned o0, unsigned) { r.g = ldg128u_pinned(row + o0); }
+
+__device__ __forceinline__ void row_unpack(const RowRaw<float>& r, f2 (&o)[4]) { unpack(r.g0, r.g1, o); }
+__device__ __forceinline__ void row_unpack(const RowRaw<__nv_bfloat16>& r, f2 (&o)[4]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.g);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = __bfloat1622float2(h[i]);
+}
+__device__ __forceinline__ void row_unpack(const RowRaw<__half>& r, f2 (&o)[4]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&r.g);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = __half22float2(h[i]);
+}
+// the chunk's ddelta: 8 values in memory order
+template <bool kV8>
+__device__ __forceinline__ void row_store(float* p, const f2 (&v)[4], bool ok0, bool ok1) {
+    if (kV8) { if (ok0) stg256(p, v[0], v[1], v[2], v[3]); }
+    else { if (ok0) stg128(p, v[0], v[1]); if (ok1) stg128(p + 4, v[2], v[3]); }
+}
+template <bool kV8>
+__device__ __forceinline__ void row_store(__nv_bfloat16* p, const f2 (&v)[4], bool ok0, bool) {
+    uint4 o;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __float22bfloat162_rn(v[i]);
+    if (ok0) asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+}
+template <bool kV8>
+__device__ __forceinline__ void row_store(__half* p, const f2 (&v)[4], bool ok0, bool) {
+    uint4 o;
+    __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __float22half2_rn(v[i]);
+    if (ok0) asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+}
+
+template <typename T>
 struct LaneChunk {              // streamed operands of one chunk, as loaded (memory order)
-    float4 dt0, dt1, B0, B1, C0, C1;
+    RowRaw<T> dt, B, C;
     float hin;
 };
 
 }  // namespace
 
 // kV8: L % 8 == 0 and 32-byte aligned rows -- every lane's 8 positions are one aligned sector (256-bit loads and stores)
-template <bool kSoftplus, bool kV8>
+template <typename T, bool kSoftplus, bool kV8>
 __global__ void __launch_bounds__(128, 3)
 ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
     extern __shared__ __align__(16) float smem[];
@@ -182,10 +236,10 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
     const int64_t bc = ((int64_t)b * 4 + k) * L;
     const int rep = p.acc_replicas > 1 ? d % p.acc_replicas : 0;
     const int64_t acc = (((int64_t)rep * p.batch + b) * 4 + k) * L;
-    const float* __restrict__ dt_row = reinterpret_cast<const float*>(p.delta) + row;
-    float* __restrict__ ddt_row = reinterpret_cast<float*>(p.ddelta) + row;
-    const float* __restrict__ B_row = reinterpret_cast<const float*>(p.Bs) + bc;
-    const float* __restrict__ C_row = reinterpret_cast<const float*>(p.Cs) + bc;
+    const T* __restrict__ dt_row = reinterpret_cast<const T*>(p.delta) + row;
+    T* __restrict__ ddt_row = reinterpret_cast<T*>(p.ddelta) + row;
+    const T* __restrict__ B_row = reinterpret_cast<const T*>(p.Bs) + bc;
+    const T* __restrict__ C_row = reinterpret_cast<const T*>(p.Cs) + bc;
     float* __restrict__ dB_row = p.dBs + acc;
     float* __restrict__ dC_row = p.dCs + acc;
     const float* __restrict__ st_row = p.states + ((int64_t)b * 4 * D + kd) * ((int64_t)nch * 32);
@@ -219,25 +273,19 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
         // 2/3 chunks 0 -> nch-1 (address = L-1 - position).  off = element offset of the granule at the lower address.
         int off = kRev ? L - 8 - 8 * lane : (nch - 1) * kChunk + 8 * lane;
         int soff = (kRev ? 0 : (nch - 1) * 32) + lane;     // checkpoint [j][lane] of the chunk being loaded
-        const unsigned off_max = (unsigned)(L - (kV8 ? 8 : 4)), soff_max = (unsigned)((nch - 1) * 32 + lane);
+        const unsigned off_max = (unsigned)(L - ((kV8 || sizeof(T) == 2) ? 8 : 4)), soff_max = (unsigned)((nch - 1) * 32 + lane);
         // L2 prefetch ahead of the register loads: lanes 0-7 / 8-15 / 16-23 take the 128-byte lines of the dt / B / C chunk
         // rows (lanes 24-31 start so far below zero that their offset never turns non-negative)
-        const float* pf_row = lane < 8 ? dt_row : (lane < 16 ? B_row : C_row);
+        const T* pf_row = lane < 8 ? dt_row : (lane < 16 ? B_row : C_row);
         int pf_off = lane < 24 ? (kRev ? L - kChunk : (nch - 1) * kChunk) + (lane & 7) * 32 : -(1 << 30);      // walk step 0
 
-        auto load = [&](LaneChunk& c) __attribute__((always_inline)) {
+        auto load = [&](LaneChunk<T>& c) __attribute__((always_inline)) {
             // Granules outside the row (last chunk; the re-load after the final chunk) are read from a valid aligned offset
             // instead -- ONE unsigned min per granule covers both ends -- and callers neutralise what they hold.
             const unsigned o0 = min((unsigned)off, off_max), o1 = min((unsigned)(off + 4), off_max);
-            if (kV8) {
-                ldg256_pinned(dt_row + o0, c.dt0, c.dt1);
-                ldg256_pinned(B_row + o0, c.B0, c.B1);
-                ldg256_pinned(C_row + o0, c.C0, c.C1);
-            } else {
-                c.dt0 = ldg128_pinned(dt_row + o0); c.dt1 = ldg128_pinned(dt_row + o1);
-                c.B0 = ldg128_pinned(B_row + o0); c.B1 = ldg128_pinned(B_row + o1);
-                c.C0 = ldg128_pinned(C_row + o0); c.C1 = ldg128_pinned(C_row + o1);
-            }
+            row_load<kV8>(c.dt, dt_row, o0, o1);
+            row_load<kV8>(c.B, B_row, o0, o1);
+            row_load<kV8>(c.C, C_row, o0, o1);
             c.hin = ldg32_pinned(st_row + min((unsigned)soff, soff_max));
             off -= kChunk;
             soff += kRev ? 32 : -32;
@@ -247,14 +295,18 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
             if (!(XFS_LANE_DIAG & 64) && pf_off >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_row + pf_off));
         };
 
-        LaneChunk c;
+        LaneChunk<T> c;
         load(c);                        // in flight while the images are staged
         prefetch();                     // walk steps 1 and 2; every chunk then prefetches the step three ahead of it
         prefetch();
         {
-            const float* __restrict__ x = reinterpret_cast<const float*>(p.x) + ((int64_t)b * D + d) * L;
+            const T* __restrict__ x = reinterpret_cast<const T*>(p.x) + ((int64_t)b * D + d) * L;
             const float* __restrict__ dyp = reinterpret_cast<const float*>(p.dy) + ((int64_t)b * D + d) * L;
-            stage_two_images(x, dyp, xN, xT, gN, gT, H, W, L, Lb, tid);
+            if constexpr (std::is_same<T, float>::value) stage_two_images(x, dyp, xN, xT, gN, gT, H, W, L, Lb, tid);
+            else {
+                stage_image<T>(x, xN, xT, H, W, L, Lb, true, tid, 128);
+                stage_image<float>(dyp, gN, gT, H, W, L, Lb, true, tid, 128);
+            }
             cta_barrier();
         }
 
@@ -280,9 +332,9 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
             }
             // ---- consume the streamed registers: dt -> log2-scaled argument, C -> C dy, B -> B u and (after softplus) dt B
             f2 xr[4], Bv[4], Cv[4], xl[4], cd[4], Bu[4];
-            unpack(c.dt0, c.dt1, xr);
-            unpack(c.B0, c.B1, Bv);
-            unpack(c.C0, c.C1, Cv);
+            row_unpack(c.dt, xr);
+            row_unpack(c.B, Bv);
+            row_unpack(c.C, Cv);
             const float hin = c.hin;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -322,7 +374,10 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
             prefetch();
             if (kSoftplus && __any_sync(kFull, odd)) {
                 f2 Br[4];
-                unpack(ldg128(B_row + min((unsigned)o, (unsigned)(L - 4))), ldg128(B_row + min((unsigned)(o + 4), (unsigned)(L - 4))), Br);
+                RowRaw<T> braw;
+                if constexpr (std::is_same<T, float>::value) row_load<false>(braw, B_row, min((unsigned)o, (unsigned)(L - 4)), min((unsigned)(o + 4), (unsigned)(L - 4)));
+                else row_load<true>(braw, B_row, min((unsigned)o, off_max), 0u);
+                row_unpack(braw, Br);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const f2 x = mul2(xl[i], splat2(kLn2)), e = e2[i];       // delta + bias again
@@ -413,12 +468,7 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
                 dA2 = fma2(g[i], dthp[i], dA2);
                 dbias2 = add2(dbias2, dd[i]);          // dt = 0 beyond L makes these terms exactly 0 (h_prev = 0 or g = 0 there)
             }
-            if (kV8) {
-                if (!(XFS_LANE_DIAG & 2) && st0) stg256(ddt_row + o, dd[0], dd[1], dd[2], dd[3]);
-            } else {
-                if (!(XFS_LANE_DIAG & 2) && st0) stg128(ddt_row + o, dd[0], dd[1]);
-                if (!(XFS_LANE_DIAG & 2) && st1) stg128(ddt_row + o + 4, dd[2], dd[3]);
-            }
+            if (!(XFS_LANE_DIAG & 2)) row_store<kV8>(ddt_row + o, dd, st0, st1);
             if (!(XFS_LANE_DIAG & 1)) {
                 if (!LAST) red_sector_pair<kRev ? -8 : 8>(dB_row, o, lane, dBv);
                 else {
@@ -476,37 +526,52 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
     __syncthreads();
 
     // dx[p] = dN[p] + dT[w*H + h]   (CrossScanF.backward = cross-merge of du, models/csm_triton.py:208-225)
-    merge_out<float>(reinterpret_cast<float*>(p.dx) + ((int64_t)b * D + d) * L, dN, dT, H, W, tid, 128);
+    merge_out<T>(reinterpret_cast<T*>(p.dx) + ((int64_t)b * D + d) * L, dN, dT, H, W, tid, 128);
 }
 
 // ---- host side --------------------------------------------------------------------------------------------------
 bool ring_enabled();
 
-// lane-granular checkpoints are what ss2d_ring_fwd.cu writes and this kernel reads; both sides decide with this predicate
+// lane-granular checkpoints are what ss2d_ring_fwd.cu (fp32) and the lane-checkpoint instantiation of ss2d_fwd.cu (bf16 / f16 rows,
+// fp32 output) write and this kernel reads; both sides decide with this predicate
 int ss2d_lane_states(int64_t N, int64_t H, int64_t W, int dtype, int out_dtype) {
     const int64_t L = H * W;
-    return ring_enabled() && dtype == XFS_F32 && out_dtype == XFS_F32 && N == 1 && L % 4 == 0 && L > kChunk &&
-           bwd_smem(L, 1, 1) <= kSmemLimit && ring_fwd_smem(L, 1, 2) <= kSmemLimit;
+    if (!ring_enabled() || out_dtype != XFS_F32 || N != 1 || L <= kChunk || bwd_smem(L, 1, 1) > kSmemLimit) return 0;
+    if (dtype == XFS_F32) return L % 4 == 0 && ring_fwd_smem(L, 1, 2) <= kSmemLimit;
+    return L % 8 == 0;          // 16-bit rows: one 16-byte granule per lane
 }
 
-int launch_ss2d_lane_bwd(const xfs_ss2d_bwd_args& a, cudaStream_t st) {
-    if (!(aligned16(a.x) && aligned16(a.delta) && aligned16(a.Bs) && aligned16(a.Cs) && aligned16(a.dy) && aligned16(a.dx) &&
-          aligned16(a.ddelta) && aligned16(a.dBs) && aligned16(a.dCs)))
-        return XFS_ERR_ALIGN;
+template <typename T>
+static int launch_lane_bwd_t(const xfs_ss2d_bwd_args& a, cudaStream_t st) {
     const size_t smem = bwd_smem(a.H * a.W, 1, 1);
     const unsigned grid = (unsigned)(a.batch * a.D);
     auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
-    const bool v8 = (a.H * a.W) % 8 == 0 && al32(a.delta) && al32(a.Bs) && al32(a.Cs) && al32(a.ddelta);
+    const bool v8 = sizeof(T) == 4 && (a.H * a.W) % 8 == 0 && al32(a.delta) && al32(a.Bs) && al32(a.Cs) && al32(a.ddelta);
     auto go = [&](auto kern) -> int {
         if (int rc = set_smem(kern, smem)) return rc;
         kern<<<grid, 128, smem, st>>>(a);
         return 0;
     };
     int rc;
-    if (a.delta_softplus) rc = v8 ? go(ss2d_lane_bwd_kernel<true, true>) : go(ss2d_lane_bwd_kernel<true, false>);
-    else rc = v8 ? go(ss2d_lane_bwd_kernel<false, true>) : go(ss2d_lane_bwd_kernel<false, false>);
+    if constexpr (sizeof(T) == 4) {
+        if (a.delta_softplus) rc = v8 ? go(ss2d_lane_bwd_kernel<T, true, true>) : go(ss2d_lane_bwd_kernel<T, true, false>);
+        else rc = v8 ? go(ss2d_lane_bwd_kernel<T, false, true>) : go(ss2d_lane_bwd_kernel<T, false, false>);
+    } else {
+        rc = a.delta_softplus ? go(ss2d_lane_bwd_kernel<T, true, false>) : go(ss2d_lane_bwd_kernel<T, false, false>);
+    }
     if (rc) return rc;
     return check_launch();
+}
+
+int launch_ss2d_lane_bwd(const xfs_ss2d_bwd_args& a, cudaStream_t st) {
+    if (!(aligned16(a.x) && aligned16(a.delta) && aligned16(a.Bs) && aligned16(a.Cs) && aligned16(a.dy) && aligned16(a.dx) &&
+          aligned16(a.ddelta) && aligned16(a.dBs) && aligned16(a.dCs)))
+        return XFS_ERR_ALIGN;
+    switch (a.dtype) {
+        case XFS_F32: return launch_lane_bwd_t<float>(a, st);
+        case XFS_BF16: return launch_lane_bwd_t<__nv_bfloat16>(a, st);
+        default: return launch_lane_bwd_t<__half>(a, st);
+    }
 }
 
 }  // namespace xfs
