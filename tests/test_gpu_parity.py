@@ -382,6 +382,26 @@ def test_ss2d_full_size_properties(xf):
     assert rel_err(n(y_rot), n(yf.flip(2))) < TOL32
 
 
+@pytest.mark.parametrize("shape", [(1, 6, 1, 128, 128), (1, 3, 1, 120, 130), (2, 2, 1, 127, 128)])
+def test_ss2d_hires_inference_is_one_fused_launch(xf, shape):
+    """BASELINE config 5 (512^2 input: stage-1 L = 16384): without checkpoints the forward is ONE fused launch even though four
+    64 KB image buffers exceed shared memory (routes 0 / 2 take x from their ring slots, csrc/ss2d_ring_fwd.cu kBig); ragged
+    sizes put the short chunk first on the flipped routes.  With gradients the three stand-alone operators still run."""
+    from xfmamba_b200 import _lib, fusion_ops
+    Bsz, D, N, H, W = shape
+    rng = np.random.default_rng(abs(hash(shape)) % 2**32)
+    c = _rand_ss2d(rng, Bsz, D, N, H, W, model_like=True)
+    assert fusion_ops.ss2d_fused_supported(D, N, H, W, torch.float32, backward=False)
+    assert not fusion_ops.ss2d_fused_supported(D, N, H, W, torch.float32, backward=True)
+    args = [t(c[k]) for k in SS2D_KEYS]
+    before = _lib.launch_count()
+    with torch.no_grad():
+        y = xf.ss2d_scan(*args)
+    assert _lib.launch_count() - before == 1
+    ref = oracle.ss2d_fwd(c["x"], c["delta"], c["A"], c["Bs"], c["Cs"], c["Ds"], c["delta_bias"], True, "f64")
+    assert rel_err(n(y), ref) < TOL32
+
+
 @pytest.mark.parametrize("shape", [(1, 3, 1, 20, 24), (2, 2, 1, 13, 20), (1, 4, 1, 14, 14)])
 def test_ss2d_softplus_outliers_vs_oracle(xf, shape):
     """softplus regimes the fast lg2(1 + e) form does not cover, mixed inside single chunks: delta + bias far below zero (the

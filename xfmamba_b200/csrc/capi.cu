@@ -13,6 +13,8 @@ int launch_scan_fwd(const xfs_scan_fwd_args&, cudaStream_t);
 int launch_scan_bwd(const xfs_scan_bwd_args&, cudaStream_t);
 int launch_ss2d_fwd(const xfs_ss2d_fwd_args&, cudaStream_t);
 int launch_ss2d_fwd_lane16(const xfs_ss2d_fwd_args&, cudaStream_t);
+int ss2d_ring_big_shape(int64_t, int64_t, int64_t, int);
+int launch_ss2d_ring_big_fwd(const xfs_ss2d_fwd_args&, cudaStream_t);
 int launch_ss2d_bwd(const xfs_ss2d_bwd_args&, cudaStream_t);
 int ss2d_supported(int64_t, int64_t, int64_t, int64_t, int, int);
 int ss2d_small_supported(int64_t, int64_t, int64_t);
@@ -145,7 +147,8 @@ int xfs_selective_scan_bwd(const xfs_scan_bwd_args* a, xfs_stream_t stream) {
 
 int xfs_ss2d_supported(int64_t D, int64_t N, int64_t H, int64_t W, int dtype, int backward) {
     if (D <= 0 || N <= 0 || H <= 0 || W <= 0 || bad_dtype(dtype)) return 0;
-    return ss2d_small_supported(N, H, W) || ss2d_supported(D, N, H, W, dtype, backward);
+    return ss2d_small_supported(N, H, W) || ss2d_supported(D, N, H, W, dtype, backward) ||
+           (!backward && ss2d_ring_big_shape(N, H, W, dtype));       // forward without checkpoints up to L = 16640 (512^2 input, stage 1)
 }
 
 int64_t xfs_ss2d_states_len(int64_t N, int64_t H, int64_t W, int dtype, int out_dtype) {
@@ -172,7 +175,11 @@ int xfs_ss2d_fwd(const xfs_ss2d_fwd_args* a, xfs_stream_t stream) {
     if (ss2d_ring_fwd_supported(*a) && (a->states == nullptr || lane_states)) return launch_ss2d_ring_fwd(*a, (cudaStream_t)stream);
     if (a->states != nullptr && lane_states)       // lane-checkpoint path: 16-bit rows take the register-fed kernel; fp32 rows get here only when misaligned
         return a->dtype == XFS_F32 ? XFS_ERR_ALIGN : launch_ss2d_fwd_lane16(*a, (cudaStream_t)stream);
-    if (!ss2d_supported(a->D, a->N, a->H, a->W, a->dtype, 0)) return XFS_ERR_UNSUPPORTED;
+    if (!ss2d_supported(a->D, a->N, a->H, a->W, a->dtype, 0)) {
+        if (a->states == nullptr && a->out_dtype == XFS_F32 && ss2d_ring_big_shape(a->N, a->H, a->W, a->dtype))
+            return launch_ss2d_ring_big_fwd(*a, (cudaStream_t)stream);
+        return XFS_ERR_UNSUPPORTED;
+    }
     return launch_ss2d_fwd(*a, (cudaStream_t)stream);
 }
 

@@ -40,12 +40,16 @@ template <int kDiag> __device__ __forceinline__ f2 dfma2(f2 a, f2 b, f2 c) {
 
 constexpr int kPrefetchCtas = 3 * 148;      // CTAs resident on the GPU at one time (3 per SM)
 
-template <bool kSoftplus, int kDiag = 0>
-__global__ void __launch_bounds__(128, 3)
+// kBig: images whose four buffers do not fit (512^2 input, stage 1: L = 16384 -> 4 x 64 KB).  The row-major image copy is
+// dropped: the bulk copy of x lands in the (not yet used) yN buffer, is transposed into xT from there, and routes 0 / 2 take
+// their u from a fourth row of their ring slots -- a 1 KB window of x in position order, copied chunk by chunk like delta /
+// B / C.  Three 64 KB buffers + 32 KB of ring: one CTA of four warps per SM, inference only (no checkpoints written).
+template <bool kSoftplus, int kDiag = 0, bool kBig = false>
+__global__ void __launch_bounds__(128, kBig ? 1 : 3)
 ss2d_ring_fwd_kernel(const xfs_ss2d_fwd_args p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int kSlots = 2;
-    constexpr uint32_t kSlotBytes = kRows * kChunkBytesF32;
+    constexpr uint32_t kSlotBytes = (kRows + (kBig ? 1 : 0)) * kChunkBytesF32;
     const int H = (int)p.H, W = (int)p.W, L = H * W;
     const int Lb = (int)buf_len(L);
     const int nch = (L + kChunk - 1) / kChunk;
@@ -57,10 +61,10 @@ ss2d_ring_fwd_kernel(const xfs_ss2d_fwd_args p) {
     const bool transposed = k & 1;
     const bool rev = k >= 2;
 
-    float* xN = reinterpret_cast<float*>(smem_raw);
-    float* xT = xN + Lb;
+    float* xT = reinterpret_cast<float*>(smem_raw) + (kBig ? 0 : Lb);
     float* yN = xT + Lb;
     float* yT = yN + Lb;
+    float* xN = kBig ? yN : reinterpret_cast<float*>(smem_raw);      // kBig: staged in yN, dead once xT is built
     unsigned char* ring_mem = reinterpret_cast<unsigned char*>(yT + Lb);        // [4 warps][kSlots][3 rows][1 KB]
     uint64_t* bars = reinterpret_cast<uint64_t*>(ring_mem + 4 * kSlots * kSlotBytes);
     const uint32_t img_bar = s32(bars);
@@ -79,7 +83,7 @@ ss2d_ring_fwd_kernel(const xfs_ss2d_fwd_args p) {
         mbar_fence_init();
         // ... and pull what a CTA about one CTA-lifetime behind this one will ask for first into L2: its image and the
         // heads of its four delta rows (B / C rows are shared by all channels of an image and stay L2 resident anyway)
-        const int64_t nb = (int64_t)blockIdx.x + kPrefetchCtas;
+        const int64_t nb = (int64_t)blockIdx.x + (kBig ? 148 : kPrefetchCtas);
         if (nb < (int64_t)gridDim.x) {
             const int64_t b2 = nb / D, d2 = nb - b2 * D;
             bulk_prefetch_l2(reinterpret_cast<const float*>(p.x) + (b2 * D + d2) * L, (uint32_t)L * 4u);
@@ -100,6 +104,9 @@ ss2d_ring_fwd_kernel(const xfs_ss2d_fwd_args p) {
     const float* f_C = reinterpret_cast<const float*>(p.Cs) + ((int64_t)b * 4 + k) * L + off0;
     int f_left = nch;                  // chunks not yet requested
     int f_rem = L * 4 - (rev ? 0 : 0); // bytes of the row not yet requested (forward routes end with the short chunk)
+    // kBig, routes 0 / 2: the window of x in POSITION order that belongs to the chunk being requested (a flipped route walks it downwards)
+    const bool xwin = kBig && !transposed;
+    const float* f_x = reinterpret_cast<const float*>(p.x) + ((int64_t)b * D + d) * L + (rev ? (nch - 1) * kChunk : 0);
 
     // One lane per warp feeds the warp's ring.  Every operand is warp-uniform (uniform registers); the running pointers
     // advance by one chunk per call, so a call is ~15 instructions: arm the mbarrier, three bulk copies, three adds.
@@ -108,24 +115,28 @@ ss2d_ring_fwd_kernel(const xfs_ss2d_fwd_args p) {
         const uint32_t bytes = (uint32_t)min(f_rem, kChunkBytesF32);
         const uint32_t bar = my_bars + 8u * slot, dst = my_ring + slot * kSlotBytes;
         if (elect_one()) {
-            mbar_expect_tx(bar, 3u * bytes);
+            mbar_expect_tx(bar, (xwin ? 4u : 3u) * bytes);
             bulk_g2s(dst, f_dt, bytes, bar);
             bulk_g2s(dst + kChunkBytesF32, f_B, bytes, bar);
             bulk_g2s(dst + 2 * kChunkBytesF32, f_C, bytes, bar);
+            if (xwin) bulk_g2s(dst + 3 * kChunkBytesF32, f_x, bytes, bar);
         }
         f_dt += kChunk; f_B += kChunk; f_C += kChunk;
+        f_x += rev ? -kChunk : kChunk;
         f_rem -= kChunkBytesF32; --f_left;
     };
 
     if (rev && off0 < 0) {             // the short chunk comes first: its data goes to the END of slot 0
         const uint32_t skip = (uint32_t)(-off0) * 4u, bytes = kChunkBytesF32 - skip;
         if (!(kDiag & 1) && elect_one()) {
-            mbar_expect_tx(my_bars, 3u * bytes);
+            mbar_expect_tx(my_bars, (xwin ? 4u : 3u) * bytes);
             bulk_g2s(my_ring + skip, f_dt - off0, bytes, my_bars);
             bulk_g2s(my_ring + skip + kChunkBytesF32, f_B - off0, bytes, my_bars);
             bulk_g2s(my_ring + skip + 2 * kChunkBytesF32, f_C - off0, bytes, my_bars);
+            if (xwin) bulk_g2s(my_ring + 3 * kChunkBytesF32, f_x, bytes, my_bars);      // position order: the short chunk sits at the window's start
         }
         f_dt += kChunk; f_B += kChunk; f_C += kChunk;
+        f_x -= kChunk;
         f_rem -= (int)bytes; --f_left;
     } else {
         fill(0);
@@ -174,7 +185,14 @@ ss2d_ring_fwd_kernel(const xfs_ss2d_fwd_args p) {
         half_from<R>(lds128(sb + 2 * kChunkBytesF32 + o.rowB), Cv[2], Cv[3]);
         {
             float4 gA = make_float4(0.f, 0.f, 0.f, 0.f), gB = gA;
-            if (!(kDiag & 8)) {
+            if (kBig && !transposed) {          // u from the slot's x window (position order: the image offsets of a linear buffer)
+                gA = lds128(sb + 3 * kChunkBytesF32 + o.imgA);
+                gB = lds128(sb + 3 * kChunkBytesF32 + o.imgB);
+                if (LAST) {                      // beyond the copied bytes the window holds stale data
+                    if (!okA) gA = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (!okB) gB = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            } else if (!(kDiag & 8)) {
                 if (!LAST || inA) gA = lds128(xb + ib + o.imgA);
                 if (!LAST || inB) gB = lds128(xb + ib + o.imgB);
             } else { gA = make_float4(dt[0].x, dt[0].y, dt[1].x, dt[1].y); gB = make_float4(dt[2].x, dt[2].y, dt[3].x, dt[3].y); }
@@ -311,6 +329,30 @@ int ss2d_ring_fwd_supported(const xfs_ss2d_fwd_args& a) {
     return ring_enabled() && a.dtype == XFS_F32 && a.out_dtype == XFS_F32 && a.N == 1 && a.scans == 0 && L % 4 == 0 && L > kChunk &&
            L <= (1 << 22) && aligned16(a.x) && aligned16(a.delta) && aligned16(a.Bs) && aligned16(a.Cs) && aligned16(a.y) &&
            ring_fwd_smem(L, 1, 2) <= kSmemLimit;
+}
+
+inline size_t ring_fwd_big_smem(int64_t L) {        // xT, yN, yT + four rows per slot
+    return sizeof(float) * (size_t)(3 * buf_len(L)) + (size_t)(4 * 2 * 4 * kChunkBytesF32) + 8 * (size_t)(1 + 4 * 2 + 8) + 8 * sizeof(float);
+}
+// shape-only predicate (xfs_ss2d_supported): forward without checkpoints of an image whose four buffers exceed shared memory
+int ss2d_ring_big_shape(int64_t N, int64_t H, int64_t W, int dtype) {
+    const int64_t L = H * W;
+    return ring_enabled() && dtype == XFS_F32 && N == 1 && L % 4 == 0 && L > kChunk && L <= (1 << 22) &&
+           ring_fwd_smem(L, 1, 2) > kSmemLimit && ring_fwd_big_smem(L) <= kSmemLimit;
+}
+int launch_ss2d_ring_big_fwd(const xfs_ss2d_fwd_args& a, cudaStream_t st) {
+    if (!(aligned16(a.x) && aligned16(a.delta) && aligned16(a.Bs) && aligned16(a.Cs) && aligned16(a.y))) return XFS_ERR_ALIGN;
+    if (a.states != nullptr || a.out_dtype != XFS_F32) return XFS_ERR_UNSUPPORTED;
+    const size_t smem = ring_fwd_big_smem(a.H * a.W);
+    const unsigned grid = (unsigned)(a.batch * a.D);
+    if (a.delta_softplus) {
+        if (int rc = set_smem(ss2d_ring_fwd_kernel<true, 0, true>, smem)) return rc;
+        ss2d_ring_fwd_kernel<true, 0, true><<<grid, 128, smem, st>>>(a);
+    } else {
+        if (int rc = set_smem(ss2d_ring_fwd_kernel<false, 0, true>, smem)) return rc;
+        ss2d_ring_fwd_kernel<false, 0, true><<<grid, 128, smem, st>>>(a);
+    }
+    return check_launch();
 }
 
 template <bool kSoftplus, int kDiag = 0>
