@@ -10,7 +10,8 @@ GPUs every rank runs the same per-GPU batch (weak scaling, batch sharded) and th
 The timed region repeats the K-step block until it is at least one second long (`inner_repeats` in the JSON line;
 ms_per_step is per step), so that clocks are sampled a few hundred times.  After the micro-benchmark every rank also runs
 BASELINE config 4 -- an XFMamba-B training step (32 pairs per GPU, DDP + NCCL all-reduce of the 104 M-parameter gradient) --
-and reports it as `model_train` (pairs/s, ms per step, exposed all-reduce time); `--no-model` skips that leg.
+and reports it as `model_train` (pairs/s, ms per step, exposed all-reduce time); rank 0 also times the cross-view fusion
+scans at their XFMamba-B shapes (7x7 tokens, N = 16) against their MUFU roofline (`fusion_blocks`); `--no-model` skips both.
 
 The JSON line carries: value (pairs/s, inputs resident in HBM), e2e (same step through the public autograd API with
 pinned HOST buffers: H2D of every input + D2H of a scalar each step), roofline of the dominant kernel (fused backward)
@@ -125,6 +126,66 @@ def cpu_threads():
     import oracle
     cores = os.cpu_count() or 1
     return oracle.set_threads(cores)
+
+
+def fusion_leg(dev, sm_mhz):
+    """The cross-view fusion scans at their XFMamba-B shapes (7x7 tokens, N = 16; models/fusion_vmamba.py:446-578, 777-845):
+    the three Cross_SS2Dv5 streams in one launch and the shallow swap scan in one kernel.  These are NOT HBM-bound: every
+    (b, k, d, l) needs N + 2 MUFU operations (exp per state, softplus), so the roofline is the MUFU pipe (16 lanes / clk / SM)."""
+    import torch
+    from xfmamba_b200 import fusion_ops
+    B, D, H, W, N = 32, 2048, 7, 7, 16
+    L = H * W
+    g = torch.Generator(device=dev).manual_seed(0)
+    mk = lambda *s_: torch.randn(*s_, device=dev, generator=g)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    def timeit(fn, iters=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters * 1e3
+
+    xs = [mk(B, D, H, W) for _ in range(3)]
+    ds = [0.5 * torch.rand(B, 4 * D, L, device=dev, generator=g) for _ in range(3)]
+    Bs = [mk(B, 4, N, L) for _ in range(3)]
+    Cs = mk(B, 4, N, L)
+    A = -0.5 * torch.rand(4 * D, N, device=dev, generator=g)
+    Ds, bias = mk(4 * D), 0.5 * torch.rand(4 * D, device=dev, generator=g)
+    dys = [mk(B, D, L) for _ in range(3)]
+    lv = [t.clone().requires_grad_(True) for t in xs]
+
+    def x3_fwd():
+        with torch.no_grad():
+            return fusion_ops.cross_ss2d_x3(xs, ds, Bs, Cs, A, Ds, bias)
+
+    def x3_fb():
+        torch.autograd.backward(fusion_ops.cross_ss2d_x3(lv, ds, Bs, Cs, A, Ds, bias), dys)
+
+    t_f, t_fb = timeit(x3_fwd), timeit(x3_fb)
+    x, x2 = mk(B, D, L), mk(B, D, L)
+    d2 = 0.5 * torch.rand(B, 2 * D, L, device=dev, generator=g)
+    B2, C2 = mk(B, 2, N, L), mk(B, 2, N, L)
+    A2 = -0.5 * torch.rand(2 * D, N, device=dev, generator=g)
+    D2, b2 = mk(2 * D), 0.5 * torch.rand(2 * D, device=dev, generator=g)
+
+    def swap_fwd():
+        with torch.no_grad():
+            return fusion_ops.swap_scan_fused(x, x2, d2, A2, B2, C2, D2, b2)
+
+    t_s = timeit(swap_fwd)
+    mufu_us = lambda elems: elems * (N + 2) / (148 * 16 * sm_mhz * 1e6) * 1e6
+    f_x3, f_sw = mufu_us(3 * B * 4 * D * L), mufu_us(B * 2 * D * L)
+    return {"shape": {"pairs": B, "d_inner": D, "H": H, "W": W, "d_state": N}, "bound": "mufu",
+            "mufu_per_element": N + 2, "deep_x3_fwd_us": t_f, "deep_x3_fwd_bwd_us": t_fb, "deep_x3_fwd_mufu_floor_us": f_x3,
+            "deep_x3_fwd_frac": f_x3 / t_f, "shallow_swap_scan_fwd_us": t_s, "shallow_fwd_mufu_floor_us": f_sw,
+            "shallow_fwd_frac": f_sw / t_s, "launches": {"deep_fwd": 1, "deep_bwd": 1, "shallow_fwd": 1}}
 
 
 def cpu_baseline(sample_batch, reps=1):
@@ -387,6 +448,11 @@ def run_ours(args):
             line["model_train"] = bench_model.train_leg("xfmamba_b_train", args.model_batch, args.model_steps, 3, dev, world, rank, local)
         except Exception as e:                      # never lose the micro-benchmark line over the model leg
             line["model_train"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    if rank == 0 and not args.no_model:
+        try:
+            line["fusion_blocks"] = fusion_leg(dev, line["clocks"].get("sm_mhz") or 1965)
+        except Exception as e:
+            line["fusion_blocks"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank == 0:
         if world == 1 and not args.no_cpu:
             cores = cpu_threads()
