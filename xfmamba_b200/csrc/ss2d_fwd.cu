@@ -174,13 +174,9 @@ ss2d_fwd_kernel(const xfs_ss2d_fwd_args p) {
             // ---- dt = softplus(delta + bias); y starts as D*u
 #pragma unroll
             for (int ch = 0; ch < kCh; ++ch) {
+                if (p.delta_softplus) softplus8_vote(dt2[ch]);
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    const f2 xx = dt2[ch][jj];
-                    f2 e;
-                    dt2[ch][jj] = p.delta_softplus ? softplus2(xx, e) : xx;
-                    y2[ch][jj] = mul2(splat2(Dd[ch]), u2[ch][jj]);
-                }
+                for (int jj = 0; jj < 4; ++jj) y2[ch][jj] = mul2(splat2(Dd[ch]), u2[ch][jj]);
             }
             // positions >= L (last chunk only): a forward route meets them after every real position, so whatever they hold
             // never reaches a real one; a flipped route had them turned into identity maps by the peeled load.
@@ -227,7 +223,7 @@ ss2d_fwd_kernel(const xfs_ss2d_fwd_args p) {
                     float* hs = s_h + (k * kCh + ch) * kFusedMaxState + n;
                     const float carry = (kN == 1) ? carry1[ch] : *hs;
                     float h_out;
-                    const float h_in = warp_prefix<rev>(Pr, Sr, carry, lane, h_out);
+                    const float h_in = warp_prefix_p<rev>(Pr, Sr, carry, lane, h_out);
                     const f2 hin2 = splat2(h_in);
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) y2[ch][jj] = fma2(C2[jj], fma2(P2[jj], hin2, S2[jj]), y2[ch][jj]);

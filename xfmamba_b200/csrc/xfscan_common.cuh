@@ -342,6 +342,37 @@ __device__ __forceinline__ f2 softplus2(f2 x, f2& e_out) {
     return r;
 }
 
+// softplus of a lane's 8 values in place, for a fully converged warp: the fast lg2(1 + e) form for everybody, and ONE warp vote
+// decides whether any element needs the small-argument series (e < 2^-6) or the x > 20 identity of softplus2 (the selects of
+// softplus2 cost ~5 instructions per element on the common path)
+__device__ __forceinline__ void softplus8_vote(f2 (&x)[4]) {
+    f2 e[4], r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        e[i] = ex2_2(mul2(x[i], splat2(kLog2e)));
+        const f2 w = add2(e[i], splat2(1.0f));
+        r[i] = mul2(make_float2(lg2(w.x), lg2(w.y)), splat2(kLn2));
+    }
+    const float emin = fminf(fminf(fminf(e[0].x, e[0].y), fminf(e[1].x, e[1].y)), fminf(fminf(e[2].x, e[2].y), fminf(e[3].x, e[3].y)));
+    const float emax = fmaxf(fmaxf(fmaxf(e[0].x, e[0].y), fmaxf(e[1].x, e[1].y)), fmaxf(fmaxf(e[2].x, e[2].y), fmaxf(e[3].x, e[3].y)));
+    if (__any_sync(kFull, !(emin >= 0.015625f && emax <= 268435456.0f))) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            f2 ser = fma2(e[i], splat2(-0.25f), splat2(0.33333334f));
+            ser = fma2(ser, e[i], splat2(-0.5f));
+            ser = fma2(ser, e[i], splat2(1.0f));
+            ser = mul2(ser, e[i]);
+            f2 q;
+            q.x = (e[i].x < 0.015625f) ? ser.x : r[i].x;
+            q.y = (e[i].y < 0.015625f) ? ser.y : r[i].y;
+            r[i].x = (x[i].x > 20.0f) ? x[i].x : q.x;
+            r[i].y = (x[i].y > 20.0f) ? x[i].y : q.y;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) x[i] = r[i];
+}
+
 // 16-byte vector reduction into global memory (sm_90+): one L2 atomic op for 4 consecutive floats
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
