@@ -313,9 +313,9 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
         f2 dD2 = splat2(0.0f), dbias2 = splat2(0.0f), dA2 = splat2(0.0f);
         float qcarry = 0.0f;
 
-        auto chunk = [&](uint32_t ib, auto last_tag, auto first_tag) __attribute__((always_inline)) {
+        auto chunk = [&](uint32_t ib, auto last_tag, const bool FIRST) __attribute__((always_inline)) {
             constexpr bool LAST = decltype(last_tag)::value;       // chunk nch-1: may hold positions >= L
-            constexpr bool FIRST = decltype(first_tag)::value;     // first touch of the pair's du accumulator: plain stores
+            // FIRST (run time: one loop body serves both halves of the walk -- half the hot code): first touch of the pair's du accumulator
             // ---- shared-memory operands: position order in the buffers, memory order (u, dy) for the arithmetic
             f2 u[4], dy[4], dyp[4];
             {
@@ -496,22 +496,23 @@ ss2d_lane_bwd_kernel(const xfs_ss2d_bwd_args p) {
         if (XFS_LANE_DIAG & 32) { pair_barrier(k & 1); }
         else if (!kRev) {                   // chunks nch-1 -> 0; first touches [m, nch)
             uint32_t ib = (uint32_t)(nch - 1) * (kChunk * 4);
-            chunk(ib, T, T);
-            int j = nch - 2;
+            chunk(ib, T, true);
 #pragma unroll 1
-            for (; j >= m; --j) { ib -= kChunk * 4; chunk(ib, F, T); }
-            pair_barrier(k & 1);
-#pragma unroll 1
-            for (; j >= 0; --j) { ib -= kChunk * 4; chunk(ib, F, F); }
+            for (int j = nch - 2; j >= 0; --j) {
+                if (j == m - 1) pair_barrier(k & 1);
+                ib -= kChunk * 4;
+                chunk(ib, F, j >= m);
+            }
         } else {                       // chunks 0 -> nch-1; first touches [0, m)
             uint32_t ib = 0;
-            int j = 0;
 #pragma unroll 1
-            for (; j < m; ++j) { chunk(ib, F, T); ib += kChunk * 4; }
-            pair_barrier(k & 1);
-#pragma unroll 1
-            for (; j < nch - 1; ++j) { chunk(ib, F, F); ib += kChunk * 4; }
-            chunk(ib, T, F);
+            for (int j = 0; j < nch - 1; ++j) {
+                if (j == m) pair_barrier(k & 1);
+                chunk(ib, F, j < m);
+                ib += kChunk * 4;
+            }
+            if (m >= nch - 1) pair_barrier(k & 1);
+            chunk(ib, T, false);
         }
 
         // parameter gradients of this route
