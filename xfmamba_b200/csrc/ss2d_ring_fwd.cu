@@ -163,10 +163,10 @@ ss2d_ring_fwd_kernel(const xfs_ss2d_fwd_args p) {
     const int st_inc = rev ? -32 : 32;
     float carry = 0.0f;
 
-    auto chunk = [&](int step, uint32_t ib, auto rev_tag, auto last_tag, auto first_tag) __attribute__((always_inline)) {
+    auto chunk = [&](int step, uint32_t ib, auto rev_tag, auto last_tag, const bool FIRST) __attribute__((always_inline)) {
         constexpr bool R = decltype(rev_tag)::value;
         constexpr bool LAST = decltype(last_tag)::value;      // the chunk that may hold positions >= L
-        constexpr bool FIRST = decltype(first_tag)::value;    // first touch of the pair's accumulator: plain stores
+        // FIRST (run time: one loop body for both halves of the walk): first touch of the pair's accumulator, plain stores
         const uint32_t slot = (uint32_t)step & 1u;
         const uint32_t sb = my_ring + slot * kSlotBytes;
         bool inA = true, inB = true, okA = true, okB = true;
@@ -288,29 +288,28 @@ ss2d_ring_fwd_kernel(const xfs_ss2d_fwd_args p) {
     if (kDiag & 32) {                  // no walk at all: what the prologue and the epilogue cost on their own
         pair_barrier(k & 1);
     } else if (rev) {
+        // steps 0 .. nch-1 = chunks nch-1 .. 0; step 0 is the short chunk (always a first touch); first touches: steps [0, n_first)
         uint32_t ib = (uint32_t)(nch - 1) * kChunkBytesF32;
-        chunk(0, ib, T, T, T);
-        int step = 1;
+        chunk(0, ib, T, T, true);
 #pragma unroll 1
-        for (; step < n_first; ++step) { ib -= kChunkBytesF32; chunk(step, ib, T, F, T); }
-        pair_barrier(k & 1);
-#pragma unroll 1
-        for (; step < nch; ++step) { ib -= kChunkBytesF32; chunk(step, ib, T, F, F); }
+        for (int step = 1; step < nch; ++step) {
+            if (step == n_first) pair_barrier(k & 1);
+            ib -= kChunkBytesF32;
+            chunk(step, ib, T, F, step < n_first);
+        }
+        if (n_first >= nch) pair_barrier(k & 1);
     } else {
+        // steps = chunks 0 .. nch-1; first touches [0, n_first) (n_first <= nch - 1: nch >= 2 here); the short chunk is the last step
         uint32_t ib = 0;
         int step = 0;
-        const int n1 = min(n_first, nch - 1);
 #pragma unroll 1
-        for (; step < n1; ++step) { chunk(step, ib, F, F, T); ib += kChunkBytesF32; }
-        if (n_first == nch) {           // single chunk: it is both the first touch and the short chunk
-            chunk(step, ib, F, T, T);
-            pair_barrier(k & 1);
-        } else {
-            pair_barrier(k & 1);
-#pragma unroll 1
-            for (; step < nch - 1; ++step) { chunk(step, ib, F, F, F); ib += kChunkBytesF32; }
-            chunk(step, ib, F, T, F);
+        for (; step < nch - 1; ++step) {
+            if (step == n_first) pair_barrier(k & 1);
+            chunk(step, ib, F, F, step < n_first);
+            ib += kChunkBytesF32;
         }
+        if (n_first >= nch - 1) pair_barrier(k & 1);
+        chunk(step, ib, F, T, n_first >= nch);
     }
     __syncthreads();
 
