@@ -195,6 +195,30 @@ def test_selective_scan_reference_grid_fp32(xf, seqlen, groups):
         assert rel_err(n(leaves[k].grad), gr) < TOL32, f"d{k}"
 
 
+@pytest.mark.parametrize("seqlen", [72, 256, 264, 784, 3136, 4104])
+@pytest.mark.parametrize("groups", [1, 4])
+@pytest.mark.parametrize("softplus", [True, False])
+def test_selective_scan_dstate1_vs_oracle(xf, seqlen, groups, softplus):
+    """d_state = 1, fp32, L % 8 == 0: what `selective_scan_fn` sees in every VMamba-style SS2D block (K = 4 groups,
+    models/fusion_vmamba.py:1170-1174), served by the 256-bit / packed backward kernel (csrc/selective_scan.cu sscan_n1_bwd_kernel).
+    Short chunk last (264, 4104), one chunk (72, 256), softplus outliers (series below 2^-6, identity above 20) mixed in."""
+    rng = np.random.default_rng(seqlen * 100 + groups * 2 + int(softplus))
+    c = _rand_scan(rng, 2, groups, 12 // groups, 1, seqlen)
+    if softplus:
+        pick = rng.integers(0, 8, size=c["delta"].shape)
+        c["delta"] = np.where(pick == 0, -11.0, np.where(pick == 1, 21.0, c["delta"])).astype(np.float32)
+        c["A"] = (0.05 * c["A"]).astype(np.float32)
+    leaves = {k: t(c[k]).requires_grad_(True) for k in GRAD_KEYS}
+    out = xf.selective_scan_fn(leaves["u"], leaves["delta"], leaves["A"], leaves["B"], leaves["C"], leaves["D"],
+                               leaves["delta_bias"], softplus, True)
+    ref = oracle.selective_scan_fwd(c["u"], c["delta"], c["A"], c["B"], c["C"], c["D"], c["delta_bias"], softplus, "f64")
+    assert rel_err(n(out), ref) < TOL32
+    out.backward(t(c["dout"]))
+    grads = oracle.selective_scan_bwd(c["u"], c["delta"], c["A"], c["B"], c["C"], c["D"], c["delta_bias"], c["dout"], softplus, "f64")
+    for k, gr in zip(GRAD_KEYS, grads):
+        assert rel_err(n(leaves[k].grad), gr) < TOL32, f"d{k}"
+
+
 @pytest.mark.parametrize("flags", [(False, False, False), (True, False, True), (False, True, False), (False, True, True)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 def test_selective_scan_flags_and_dtypes(xf, flags, dtype):

@@ -242,6 +242,212 @@ sscan_bwd_kernel(const xfs_scan_bwd_args p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// backward, N == 1, fp32 rows, L % 8 == 0, 32-byte aligned tensors: what `selective_scan_fn` sees in every VMamba-style block
+// (d_state = 1; reference models/csms6s.py:71-126 -> selective_scan_bwd_kernel.cuh).  Same arithmetic as ss2d_lane_bwd.cu:
+// 256-bit loads of the NEXT chunk's five rows (u, delta, dout, B, C) issued before the rare softplus-repair branch, packed
+// FFMA2 / FMUL2 arithmetic, the adjoint folded as G_i = cd_i + a_{i+1} G_{i+1} with suffix products, ONE interleaved pair of
+// predicate-out warp scans (forward fold from the chunk checkpoint, adjoint against it), everything that does not depend on
+// the adjoint computed in front of the scan.  The general kernel above loads at the top of every chunk (latency exposed)
+// and computes in scalar fp32.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ void ldg256p(const float* p, f2 (&o)[4]) {
+    asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(o[0].x), "=f"(o[0].y), "=f"(o[1].x), "=f"(o[1].y), "=f"(o[2].x), "=f"(o[2].y), "=f"(o[3].x), "=f"(o[3].y) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void stg256p(float* p, const f2 (&v)[4]) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0].x), "f"(v[0].y), "f"(v[1].x), "f"(v[1].y),
+                 "f"(v[2].x), "f"(v[2].y), "f"(v[3].x), "f"(v[3].y) : "memory");
+}
+__device__ __forceinline__ float& el8(f2 (&v)[4], int i) { return (i & 1) ? v[i >> 1].y : v[i >> 1].x; }
+struct N1Chunk { f2 u[4], dt[4], dy[4], B[4], C[4]; float hstart; };
+}  // namespace
+
+template <bool kSoftplus>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+sscan_n1_bwd_kernel(const xfs_scan_bwd_args p) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t work = (int64_t)blockIdx.x * kWarpsPerCta + wib;
+    if (work >= p.batch * p.dim) return;                       // whole warps only
+    const int64_t b = work % p.batch, d = work / p.batch;        // batch index fastest (see sscan_bwd_kernel)
+    const int64_t seq = b * p.dim + d;
+    const int L = (int)p.seqlen;
+    const int64_t g = d / (p.dim / p.ngroups);
+    const int nch = (L + kChunk - 1) / kChunk;
+    const float* __restrict__ u_row = reinterpret_cast<const float*>(p.u) + seq * L;
+    const float* __restrict__ dt_row = reinterpret_cast<const float*>(p.delta) + seq * L;
+    const float* __restrict__ dy_row = reinterpret_cast<const float*>(p.dout) + seq * L;
+    const float* __restrict__ B_row = reinterpret_cast<const float*>(p.B) + (b * p.ngroups + g) * L;
+    const float* __restrict__ C_row = reinterpret_cast<const float*>(p.C) + (b * p.ngroups + g) * L;
+    const int64_t rep = p.acc_replicas > 1 ? d % p.acc_replicas : 0;
+    float* __restrict__ dB_row = p.dB + ((rep * p.batch + b) * p.ngroups + g) * L;
+    float* __restrict__ dC_row = p.dC + ((rep * p.batch + b) * p.ngroups + g) * L;
+    float* __restrict__ du_row = reinterpret_cast<float*>(p.du) + seq * L;
+    float* __restrict__ ddt_row = reinterpret_cast<float*>(p.ddelta) + seq * L;
+    const float* __restrict__ st = p.states + seq * nch;
+    asm volatile("" : "+l"(u_row), "+l"(dt_row), "+l"(dy_row), "+l"(B_row), "+l"(C_row));
+    asm volatile("" : "+l"(dB_row), "+l"(dC_row), "+l"(du_row), "+l"(ddt_row), "+l"(st));
+    const float bias = p.delta_bias ? p.delta_bias[d] : 0.0f;
+    const float Dd = p.D ? p.D[d] : 0.0f;
+    const float An = p.A[d], A2 = An * kLog2e;
+    const unsigned off_max = (unsigned)(L - 8);
+
+    int off = (nch - 1) * kChunk + 8 * lane;                     // this lane's 8 positions of the chunk being loaded
+    int cidx = nch - 1;
+    auto load = [&](N1Chunk& c) __attribute__((always_inline)) {
+        const unsigned o = min((unsigned)off, off_max);            // beyond the row (last chunk) / before it (the re-load after chunk 0): clamped
+        ldg256p(dt_row + o, c.dt); ldg256p(u_row + o, c.u); ldg256p(dy_row + o, c.dy);
+        ldg256p(B_row + o, c.B); ldg256p(C_row + o, c.C);
+        float hs = 0.0f;
+        if (cidx > 0) asm volatile("ld.global.f32 %0, [%1];" : "=f"(hs) : "l"(st + (cidx - 1)) : "memory");
+        c.hstart = hs;
+        off -= kChunk; --cidx;
+    };
+    N1Chunk c;
+    load(c);
+    f2 dD2 = splat2(0.0f), dbias2 = splat2(0.0f), dA2 = splat2(0.0f);
+    float qcarry = 0.0f;
+
+#pragma unroll 1
+    for (int ci = nch - 1; ci >= 0; --ci) {
+        const int o = off + kChunk;                              // this chunk's offset
+        const bool ok = o + 8 <= L;                              // L % 8 == 0: a lane's sector is inside or outside the row
+        f2 u[4], dy[4], Bv[4], xl[4], cd[4], Bu[4], dt[4], sig[4], dtB[4], e2[4];
+        const float hstart = c.hstart;
+        bool odd = false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            u[i] = ok ? c.u[i] : splat2(0.0f);
+            dy[i] = ok ? c.dy[i] : splat2(0.0f);
+            Bv[i] = c.B[i];
+            xl[i] = kSoftplus ? fma2(c.dt[i], splat2(kLog2e), splat2(bias * kLog2e)) : add2(c.dt[i], splat2(bias));
+            cd[i] = mul2(c.C[i], dy[i]);
+            Bu[i] = mul2(Bv[i], u[i]);
+        }
+        if (kSoftplus) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                e2[i] = ex2_2(xl[i]);
+                const f2 w = add2(e2[i], splat2(1.0f));
+                dt[i] = mul2(make_float2(lg2(w.x), lg2(w.y)), splat2(kLn2));
+                sig[i] = mul2(e2[i], make_float2(rcp(w.x), rcp(w.y)));
+            }
+            const float emin = fminf(fminf(fminf(e2[0].x, e2[0].y), fminf(e2[1].x, e2[1].y)), fminf(fminf(e2[2].x, e2[2].y), fminf(e2[3].x, e2[3].y)));
+            const float emax = fmaxf(fmaxf(fmaxf(e2[0].x, e2[0].y), fmaxf(e2[1].x, e2[1].y)), fmaxf(fmaxf(e2[2].x, e2[2].y), fmaxf(e2[3].x, e2[3].y)));
+            odd = !(emin >= 0.015625f && emax <= 268435456.0f);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { dt[i] = xl[i]; sig[i] = splat2(1.0f); }
+        }
+        if (!ok) { dt[0] = dt[1] = dt[2] = dt[3] = splat2(0.0f); }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dtB[i] = mul2(dt[i], Bv[i]);
+        load(c);                                                   // every streamed register has been read: next chunk's loads, pinned here
+        __syncwarp();
+        if (kSoftplus && __any_sync(kFull, odd)) {                 // rare: small-argument series / identity above 20; B re-read from L2
+            f2 Br[4];
+            ldg256p(B_row + min((unsigned)o, off_max), Br);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const f2 x = mul2(xl[i], splat2(kLn2)), e = e2[i];
+                f2 ser = fma2(e, splat2(-0.25f), splat2(0.33333334f));
+                ser = fma2(ser, e, splat2(-0.5f));
+                ser = fma2(ser, e, splat2(1.0f));
+                ser = mul2(ser, e);
+                f2 q;
+                q.x = (e.x < 0.015625f) ? ser.x : dt[i].x;
+                q.y = (e.y < 0.015625f) ? ser.y : dt[i].y;
+                dt[i].x = (x.x > 20.0f) ? x.x : q.x;
+                dt[i].y = (x.y > 20.0f) ? x.y : q.y;
+                sig[i].x = (x.x > 20.0f) ? 1.0f : sig[i].x;
+                sig[i].y = (x.y > 20.0f) ? 1.0f : sig[i].y;
+                if (!ok) dt[i] = splat2(0.0f);
+                dtB[i] = mul2(dt[i], Br[i]);
+            }
+        }
+        // forward fold (ascending) and adjoint fold (descending) of the lane's 8 positions
+        f2 a[4], bu[4], S[4], P[4], G[4], Pq[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            a[i] = ex2_2(mul2(dt[i], splat2(A2)));
+            bu[i] = mul2(dtB[i], u[i]);
+        }
+        float Sr = 0.0f, Pr = 1.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            Sr = fmaf(el8(a, i), Sr, el8(bu, i));
+            Pr = (i == 0) ? el8(a, 0) : Pr * el8(a, i);
+            el8(S, i) = Sr; el8(P, i) = Pr;
+        }
+        float Gp = el8(cd, 7), Pp = 1.0f;
+        el8(G, 7) = Gp; el8(Pq, 7) = 1.0f;
+#pragma unroll
+        for (int i = 6; i >= 0; --i) {
+            const float an = el8(a, i + 1);
+            Gp = fmaf(an, Gp, el8(cd, i));
+            Pp = (i == 6) ? an : Pp * an;
+            el8(G, i) = Gp; el8(Pq, i) = Pp;
+        }
+        // one interleaved pair of warp scans: forward (lanes ascending, from the chunk checkpoint), adjoint (descending, from qcarry)
+        float Pf = Pr, Sf = Sr, Pa = el8(a, 0) * Pp, Sa = el8(a, 0) * Gp;
+#pragma unroll
+        for (int so = 1; so < 32; so <<= 1) {
+            asm volatile("{\n\t.reg .pred p;\n\t.reg .f32 pn, sn;\n\t"
+                         "shfl.sync.up.b32 pn|p, %0, %2, 0, 0xffffffff;\n\t"
+                         "shfl.sync.up.b32 sn, %1, %2, 0, 0xffffffff;\n\t"
+                         "@p fma.rn.ftz.f32 %1, %0, sn, %1;\n\t"
+                         "@p mul.ftz.f32 %0, %0, pn;\n\t}" : "+f"(Pf), "+f"(Sf) : "r"(so));
+            asm volatile("{\n\t.reg .pred p;\n\t.reg .f32 pn, sn;\n\t"
+                         "shfl.sync.down.b32 pn|p, %0, %2, 0x1f, 0xffffffff;\n\t"
+                         "shfl.sync.down.b32 sn, %1, %2, 0x1f, 0xffffffff;\n\t"
+                         "@p fma.rn.ftz.f32 %1, %0, sn, %1;\n\t"
+                         "@p mul.ftz.f32 %0, %0, pn;\n\t}" : "+f"(Pa), "+f"(Sa) : "r"(so));
+        }
+        const float incl_f = fmaf(Pf, hstart, Sf), incl_a = fmaf(Pa, qcarry, Sa);
+        float h_in = hstart, r_in = qcarry;
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .f32 t;\n\tshfl.sync.up.b32 t|p, %1, 1, 0, 0xffffffff;\n\t@p mov.f32 %0, t;\n\t}" : "+f"(h_in) : "f"(incl_f));
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .f32 t;\n\tshfl.sync.down.b32 t|p, %1, 1, 0x1f, 0xffffffff;\n\t@p mov.f32 %0, t;\n\t}" : "+f"(r_in) : "f"(incl_a));
+        qcarry = __shfl_sync(kFull, incl_a, 0);
+
+        f2 du[4], dd[4], dBv[4], dCv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const f2 h = fma2(P[i], splat2(h_in), S[i]);
+            const f2 hp = fma2(bu[i], splat2(-1.0f), h);               // a_i h_prev
+            const f2 gg = fma2(Pq[i], splat2(r_in), G[i]);
+            const f2 gdt = mul2(gg, dt[i]);
+            du[i] = fma2(gg, dtB[i], mul2(splat2(Dd), dy[i]));
+            dd[i] = mul2(mul2(gg, fma2(splat2(An), hp, Bu[i])), sig[i]);
+            dA2 = fma2(gdt, hp, dA2);
+            dBv[i] = mul2(gdt, u[i]);
+            dCv[i] = mul2(dy[i], h);
+            dD2 = fma2(dy[i], u[i], dD2);
+            dbias2 = add2(dbias2, dd[i]);
+        }
+        if (ok) {
+            stg256p(du_row + o, du);
+            stg256p(ddt_row + o, dd);
+            red_add_v4(dB_row + o, dBv[0].x, dBv[0].y, dBv[1].x, dBv[1].y);
+            red_add_v4(dB_row + o + 4, dBv[2].x, dBv[2].y, dBv[3].x, dBv[3].y);
+            red_add_v4(dC_row + o, dCv[0].x, dCv[0].y, dCv[1].x, dCv[1].y);
+            red_add_v4(dC_row + o + 4, dCv[2].x, dCv[2].y, dCv[3].x, dCv[3].y);
+        }
+    }
+    const float vA = warp_sum(dA2.x + dA2.y), vD = warp_sum(dD2.x + dD2.y), vb = warp_sum(dbias2.x + dbias2.y);
+    if (lane == 0) {
+        atomicAdd(p.dA + d, vA);
+        if (p.dD) atomicAdd(p.dD + d, vD);
+        if (p.ddelta_bias) atomicAdd(p.ddelta_bias + d, vb);
+    }
+}
+
+static bool n1_bwd_ok(const xfs_scan_bwd_args& a) {
+    auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
+    return a.dtype == XFS_F32 && a.dout_dtype == XFS_F32 && a.dstate == 1 && a.seqlen % 8 == 0 && a.seqlen <= (1 << 24) && al(a.u) &&
+           al(a.delta) && al(a.dout) && al(a.B) && al(a.C) && al(a.du) && al(a.ddelta) && al(a.dB) && al(a.dC);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------------------
 template <typename T>
@@ -281,6 +487,12 @@ static int launch_bwd_t(const xfs_scan_bwd_args& a, cudaStream_t st) {
 
 int launch_scan_bwd(const xfs_scan_bwd_args& a, cudaStream_t st) {
     if (scan_small_supported(a.seqlen, a.dstate)) return launch_scan_small_bwd(a, st);
+    if (n1_bwd_ok(a)) {
+        const unsigned grid = (unsigned)((a.batch * a.dim + kWarpsPerCta - 1) / kWarpsPerCta);
+        if (a.delta_softplus) sscan_n1_bwd_kernel<true><<<grid, kWarpsPerCta * 32, 0, st>>>(a);
+        else sscan_n1_bwd_kernel<false><<<grid, kWarpsPerCta * 32, 0, st>>>(a);
+        return check_launch();
+    }
     switch (a.dtype) {
         case XFS_F32: return launch_bwd_t<float>(a, st);
         case XFS_BF16: return launch_bwd_t<__nv_bfloat16>(a, st);
