@@ -441,6 +441,111 @@ sscan_n1_bwd_kernel(const xfs_scan_bwd_args p) {
     }
 }
 
+// forward twin of sscan_n1_bwd_kernel (d_state = 1, fp32 rows and output, L % 8 == 0, 32-byte aligned): the next chunk's four
+// rows in flight (256-bit loads) while this one is computed, packed arithmetic, one predicate-out warp scan
+template <bool kSoftplus>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+sscan_n1_fwd_kernel(const xfs_scan_fwd_args p) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t seq = (int64_t)blockIdx.x * kWarpsPerCta + wib;      // b*dim + d
+    if (seq >= p.batch * p.dim) return;
+    const int64_t b = seq / p.dim, d = seq % p.dim;
+    const int L = (int)p.seqlen;
+    const int64_t g = d / (p.dim / p.ngroups);
+    const int nch = (L + kChunk - 1) / kChunk;
+    const float* __restrict__ u_row = reinterpret_cast<const float*>(p.u) + seq * L;
+    const float* __restrict__ dt_row = reinterpret_cast<const float*>(p.delta) + seq * L;
+    const float* __restrict__ B_row = reinterpret_cast<const float*>(p.B) + (b * p.ngroups + g) * L;
+    const float* __restrict__ C_row = reinterpret_cast<const float*>(p.C) + (b * p.ngroups + g) * L;
+    float* __restrict__ o_row = reinterpret_cast<float*>(p.out) + seq * L;
+    float* __restrict__ st = p.states ? p.states + seq * nch : nullptr;
+    asm volatile("" : "+l"(u_row), "+l"(dt_row), "+l"(B_row), "+l"(C_row), "+l"(o_row));
+    const float bias = p.delta_bias ? p.delta_bias[d] : 0.0f;
+    const float Dd = p.D ? p.D[d] : 0.0f;
+    const float A2 = p.A[d] * kLog2e;
+    const unsigned off_max = (unsigned)(L - 8);
+    int off = 8 * lane;
+    f2 ldt[4], lu[4], lB[4], lC[4];
+    auto load = [&]() __attribute__((always_inline)) {
+        const unsigned o = min((unsigned)off, off_max);
+        ldg256p(dt_row + o, ldt); ldg256p(u_row + o, lu); ldg256p(B_row + o, lB); ldg256p(C_row + o, lC);
+        off += kChunk;
+    };
+    load();
+    float carry = 0.0f;
+#pragma unroll 1
+    for (int c = 0; c < nch; ++c) {
+        const int o = off - kChunk;
+        const bool ok = o + 8 <= L;
+        f2 u[4], Cv[4], Bu[4], dt[4], e2[4], xr[4];
+        bool odd = false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            u[i] = lu[i]; Cv[i] = lC[i]; xr[i] = ldt[i];
+            Bu[i] = mul2(lB[i], u[i]);
+        }
+        load();                                  // next chunk's rows (clamped past the end), in front of the rare branch
+        __syncwarp();
+        if (kSoftplus) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                e2[i] = ex2_2(fma2(xr[i], splat2(kLog2e), splat2(bias * kLog2e)));
+                const f2 w = add2(e2[i], splat2(1.0f));
+                dt[i] = mul2(make_float2(lg2(w.x), lg2(w.y)), splat2(kLn2));
+            }
+            const float emin = fminf(fminf(fminf(e2[0].x, e2[0].y), fminf(e2[1].x, e2[1].y)), fminf(fminf(e2[2].x, e2[2].y), fminf(e2[3].x, e2[3].y)));
+            const float emax = fmaxf(fmaxf(fmaxf(e2[0].x, e2[0].y), fmaxf(e2[1].x, e2[1].y)), fmaxf(fmaxf(e2[2].x, e2[2].y), fmaxf(e2[3].x, e2[3].y)));
+            odd = !(emin >= 0.015625f && emax <= 268435456.0f);
+            if (__any_sync(kFull, odd)) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const f2 x = add2(xr[i], splat2(bias)), e = e2[i];
+                    f2 ser = fma2(e, splat2(-0.25f), splat2(0.33333334f));
+                    ser = fma2(ser, e, splat2(-0.5f));
+                    ser = fma2(ser, e, splat2(1.0f));
+                    ser = mul2(ser, e);
+                    f2 q;
+                    q.x = (e.x < 0.015625f) ? ser.x : dt[i].x;
+                    q.y = (e.y < 0.015625f) ? ser.y : dt[i].y;
+                    dt[i].x = (x.x > 20.0f) ? x.x : q.x;
+                    dt[i].y = (x.y > 20.0f) ? x.y : q.y;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dt[i] = add2(xr[i], splat2(bias));
+        }
+        if (!ok) { dt[0] = dt[1] = dt[2] = dt[3] = splat2(0.0f); }      // identity maps beyond the end of the sequence
+        f2 a[4], bu[4], S[4], P[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            a[i] = ex2_2(mul2(dt[i], splat2(A2)));
+            bu[i] = mul2(dt[i], Bu[i]);
+        }
+        float Sr = 0.0f, Pr = 1.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            Sr = fmaf(el8(a, i), Sr, el8(bu, i));
+            Pr = (i == 0) ? el8(a, 0) : Pr * el8(a, i);
+            el8(S, i) = Sr; el8(P, i) = Pr;
+        }
+        float h_out;
+        const float h_in = warp_prefix_p<false>(Pr, Sr, carry, lane, h_out);
+        carry = h_out;
+        if (st && lane == 0) st[c] = h_out;
+        f2 y[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y[i] = fma2(Cv[i], fma2(P[i], splat2(h_in), S[i]), mul2(splat2(Dd), u[i]));
+        if (ok) stg256p(o_row + o, y);
+    }
+}
+
+static bool n1_fwd_ok(const xfs_scan_fwd_args& a) {
+    auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
+    return a.dtype == XFS_F32 && a.out_dtype == XFS_F32 && a.dstate == 1 && a.seqlen % 8 == 0 && a.seqlen <= (1 << 24) && al(a.u) &&
+           al(a.delta) && al(a.B) && al(a.C) && al(a.out);
+}
+
 static bool n1_bwd_ok(const xfs_scan_bwd_args& a) {
     auto al = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
     return a.dtype == XFS_F32 && a.dout_dtype == XFS_F32 && a.dstate == 1 && a.seqlen % 8 == 0 && a.seqlen <= (1 << 24) && al(a.u) &&
@@ -467,6 +572,12 @@ bool scan_small_supported(int64_t L, int64_t N);
 
 int launch_scan_fwd(const xfs_scan_fwd_args& a, cudaStream_t st) {
     if (scan_small_supported(a.seqlen, a.dstate)) return launch_scan_small_fwd(a, st);
+    if (n1_fwd_ok(a)) {
+        const unsigned grid = (unsigned)((a.batch * a.dim + kWarpsPerCta - 1) / kWarpsPerCta);
+        if (a.delta_softplus) sscan_n1_fwd_kernel<true><<<grid, kWarpsPerCta * 32, 0, st>>>(a);
+        else sscan_n1_fwd_kernel<false><<<grid, kWarpsPerCta * 32, 0, st>>>(a);
+        return check_launch();
+    }
     switch (a.dtype) {
         case XFS_F32: return launch_fwd_t<float>(a, st);
         case XFS_BF16: return launch_fwd_t<__nv_bfloat16>(a, st);
