@@ -124,6 +124,59 @@ __device__ __forceinline__ void lds8_lin(const float* row, int p0, float (&v)[8]
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
+// ---- a quad's rows in REGISTERS: loaded one quad ahead (in flight while the current quad is computed), stored to shared memory at
+// the top of the next step.  Warp w of the CTA owns channel w of the quad: two elements per lane and row (l = lane, lane + 32).
+struct QuadRegs {
+    float x[2], g[2], dt[4][2];
+};
+template <typename T, typename TG, bool kWithG>
+__device__ __forceinline__ void quad_load(QuadRegs& r, const T* __restrict__ x, const TG* __restrict__ gsrc, const T* __restrict__ delta,
+                                          int64_t img0, int64_t drow0, int64_t D, int nvalid, int L, int tid) {
+    const int lane = tid & 31, ch = tid >> 5;
+    const bool ok0 = ch < nvalid && lane < L, ok1 = ch < nvalid && lane + 32 < L;
+    const int64_t xo = (img0 + ch) * L;
+    r.x[0] = ok0 ? Elem<T>::to_f(x[xo + lane]) : 0.0f;
+    r.x[1] = ok1 ? Elem<T>::to_f(x[xo + lane + 32]) : 0.0f;
+    if (kWithG) {
+        r.g[0] = ok0 ? Elem<TG>::to_f(gsrc[xo + lane]) : 0.0f;
+        r.g[1] = ok1 ? Elem<TG>::to_f(gsrc[xo + lane + 32]) : 0.0f;
+    }
+#pragma unroll
+    for (int rt = 0; rt < 4; ++rt) {
+        const int64_t ro = (drow0 + (int64_t)rt * D + ch) * L;
+        r.dt[rt][0] = ok0 ? Elem<T>::to_f(delta[ro + lane]) : 0.0f;
+        r.dt[rt][1] = ok1 ? Elem<T>::to_f(delta[ro + lane + 32]) : 0.0f;
+    }
+}
+template <bool kWithG>
+__device__ __forceinline__ void quad_store(const QuadRegs& r, float* xN, float* xT, float* gN, float* gT, float* sdt, const int* tpos,
+                                           int nvalid, int L, int tid) {
+    const int lane = tid & 31, ch = tid >> 5;
+    xN[ch * kSmallL + swz_pos(lane)] = r.x[0];
+    xN[ch * kSmallL + swz_pos(lane + 32)] = r.x[1];
+    xT[ch * kSmallL + tpos[lane]] = r.x[0];
+    xT[ch * kSmallL + tpos[lane + 32]] = r.x[1];
+    if (kWithG) {
+        gN[ch * kSmallL + swz_pos(lane)] = r.g[0];
+        gN[ch * kSmallL + swz_pos(lane + 32)] = r.g[1];
+        gT[ch * kSmallL + tpos[lane]] = r.g[0];
+        gT[ch * kSmallL + tpos[lane + 32]] = r.g[1];
+    }
+    if (ch < nvalid) {
+#pragma unroll
+        for (int rt = 0; rt < 4; ++rt) {                 // position order: a flipped route walks l = L-1-p
+            float* rd = sdt + (rt * kQuad + ch) * kSmallL;
+            if (rt < 2) { rd[lane] = r.dt[rt][0]; rd[lane + 32] = r.dt[rt][1]; }
+            else {
+                if (lane < L) rd[L - 1 - lane] = r.dt[rt][0];
+                if (lane + 32 < L) rd[L - 1 - (lane + 32)] = r.dt[rt][1];
+                if (lane >= L) rd[lane] = 0.0f;
+                if (lane + 32 >= L) rd[lane + 32] = 0.0f;
+            }
+        }
+    }
+}
+
 // =========================================================================================================
 // three SS2D streams, forward
 // =========================================================================================================
@@ -160,6 +213,12 @@ fs_x3_fwd_kernel(const FsX3Fwd p) {
     const float* myB = sB + k * N * kSmallL;
     const float* myC = sC + k * N * kSmallL;
 
+    const T* __restrict__ xsrc = reinterpret_cast<const T*>(p.x[s]);
+    const T* __restrict__ dsrc = reinterpret_cast<const T*>(p.delta[s]);
+    QuadRegs qr;
+    if (q_begin < q_end)
+        quad_load<T, T, false>(qr, xsrc, xsrc, dsrc, (int64_t)b * D + q_begin * kQuad, (int64_t)b * 4 * D + q_begin * kQuad, D,
+                               min(kQuad, D - q_begin * kQuad), L, tid);
     for (int q = q_begin; q < q_end; ++q) {
         const int d0 = q * kQuad;
         const int nvalid = min(kQuad, D - d0);
@@ -167,12 +226,10 @@ fs_x3_fwd_kernel(const FsX3Fwd p) {
         const int d = d0 + (valid ? g : 0);
         const int kd = k * D + d;
         __syncthreads();                               // the previous quad's merge is done with the buffers
-        stage_quad_t<T>(reinterpret_cast<const T*>(p.x[s]) + ((int64_t)b * D + d0) * L, nvalid, xN, xT, tpos, L, tid);
-        {   // delta rows of this quad: route r, channels d0..d0+nvalid-1 are nvalid*L contiguous elements
-            const T* __restrict__ dsrc = reinterpret_cast<const T*>(p.delta[s]) + (int64_t)b * 4 * D * L;
-            for (int r = 0; r < 4; ++r)      // route r: channels d0 .. d0+nvalid-1 are nvalid rows of L contiguous elements
-                stage_rows<T>(dsrc + ((int64_t)r * D + d0) * L, sdt + r * kQuad * kSmallL, nvalid, L, r >= 2, tid, 128);
-        }
+        quad_store<false>(qr, xN, xT, nullptr, nullptr, sdt, tpos, nvalid, L, tid);
+        if (q + 1 < q_end)                             // the next quad's rows fly while this one is computed
+            quad_load<T, T, false>(qr, xsrc, xsrc, dsrc, (int64_t)b * D + d0 + kQuad, (int64_t)b * 4 * D + d0 + kQuad, D,
+                                   min(kQuad, D - d0 - kQuad), L, tid);
         __syncthreads();
 
         const float bias = p.bias ? p.bias[kd] : 0.0f;
@@ -274,6 +331,13 @@ fs_x3_bwd_kernel(const FsX3Bwd p) {
     float* mydB = sdB + k * N * kSmallL;
     float* mydC = sdC + k * N * kSmallL;
 
+    const T* __restrict__ xsrc = reinterpret_cast<const T*>(p.x[s]);
+    const TDO* __restrict__ gsrc = reinterpret_cast<const TDO*>(p.dy[s]);
+    const T* __restrict__ dsrc = reinterpret_cast<const T*>(p.delta[s]);
+    QuadRegs qr;
+    if (q_begin < q_end)
+        quad_load<T, TDO, true>(qr, xsrc, gsrc, dsrc, (int64_t)b * D + q_begin * kQuad, (int64_t)b * 4 * D + q_begin * kQuad, D,
+                                min(kQuad, D - q_begin * kQuad), L, tid);
     for (int q = q_begin; q < q_end; ++q) {
         const int d0 = q * kQuad;
         const int nvalid = min(kQuad, D - d0);
@@ -281,13 +345,10 @@ fs_x3_bwd_kernel(const FsX3Bwd p) {
         const int d = d0 + (valid ? g : 0);
         const int kd = k * D + d;
         __syncthreads();
-        stage_quad_t<T>(reinterpret_cast<const T*>(p.x[s]) + ((int64_t)b * D + d0) * L, nvalid, xN, xT, tpos, L, tid);
-        stage_quad_t<TDO>(reinterpret_cast<const TDO*>(p.dy[s]) + ((int64_t)b * D + d0) * L, nvalid, gN, gT, tpos, L, tid);
-        {
-            const T* __restrict__ dsrc = reinterpret_cast<const T*>(p.delta[s]) + (int64_t)b * 4 * D * L;
-            for (int r = 0; r < 4; ++r)      // route r: channels d0 .. d0+nvalid-1 are nvalid rows of L contiguous elements
-                stage_rows<T>(dsrc + ((int64_t)r * D + d0) * L, sdt + r * kQuad * kSmallL, nvalid, L, r >= 2, tid, 128);
-        }
+        quad_store<true>(qr, xN, xT, gN, gT, sdt, tpos, nvalid, L, tid);
+        if (q + 1 < q_end)                             // the next quad's rows fly while this one is computed
+            quad_load<T, TDO, true>(qr, xsrc, gsrc, dsrc, (int64_t)b * D + d0 + kQuad, (int64_t)b * 4 * D + d0 + kQuad, D,
+                                    min(kQuad, D - d0 - kQuad), L, tid);
         __syncthreads();
 
         const float bias = p.bias ? p.bias[kd] : 0.0f;
