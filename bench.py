@@ -188,6 +188,33 @@ def fusion_leg(dev, sm_mhz):
             "shallow_fwd_frac": f_sw / t_s, "launches": {"deep_fwd": 1, "deep_bwd": 1, "shallow_fwd": 1}}
 
 
+def ref_gpu_leg(dev, batch, ours_ms):
+    """Same-box context: the reference's own CUDA selective scan (oracle/_ref, built from /root/reference for sm_100 by
+    oracle/build_ref.py) between torch CrossScan / CrossMerge, on the bench workload; also a GPU-side parity check of the fused path."""
+    try:
+        import torch
+        from oracle import ref_gpu
+        from xfmamba_b200 import ss2d_scan
+        if not ref_gpu.available():
+            return {"unavailable": "oracle/_ref/selective_scan_cuda_core.so not built (python oracle/build_ref.py in the build container)"}
+        w = WORKLOAD
+        d = {k: torch.from_numpy(v).to(dev) for k, v in synth_inputs_np(batch, seed=0).items()}
+        t, y_ref, dy, g_ref = ref_gpu.time_config(d, w["H"], w["W"])
+        x = d["x"].clone().requires_grad_()
+        delta = d["delta"].clone().requires_grad_()
+        y = ss2d_scan(x, delta, d["A"], d["Bs"], d["Cs"], d["Ds"], d["delta_bias"], True, True)
+        dx, ddelta = torch.autograd.grad(y, (x, delta), dy.view_as(y))
+        rel = lambda a, b: float((a.detach().double() - b.double()).abs().max() / b.double().abs().max())
+        ms = t["fwd_ms"] + t["bwd_ms"]
+        return {"what": "reference selective_scan_cuda_core (sm_100 build of its own sources, oracle/build_ref.py) between torch "
+                        "CrossScan/CrossMerge (4 HBM passes), fp32, the bench inputs, device-resident",
+                **{k: round(v, 4) for k, v in t.items()}, "ms_per_step": round(ms, 4), "pairs_per_s": batch / 2 / (ms * 1e-3),
+                "ref_ms_over_ours_ms": ms / ours_ms, "scan_kernels_ms_over_ours_ms": (t["scan_fwd_ms"] + t["scan_bwd_ms"]) / ours_ms,
+                "max_rel_diff_vs_ours": {"y": rel(y.view_as(y_ref), y_ref), "dx": rel(dx.view_as(g_ref[0]), g_ref[0]), "ddelta": rel(ddelta, g_ref[1])}}
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
 def cpu_baseline(sample_batch, reps=1):
     """fwd+bwd of the same path with the CPU oracle (C, OpenMP) on `sample_batch` images; returns pairs/s"""
     import oracle
@@ -448,6 +475,8 @@ def run_ours(args):
             line["model_train"] = bench_model.train_leg("xfmamba_b_train", args.model_batch, args.model_steps, 3, dev, world, rank, local)
         except Exception as e:                      # never lose the micro-benchmark line over the model leg
             line["model_train"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    if rank == 0 and world == 1 and args.dtype == "f32" and not args.no_ref_gpu:
+        line["ref_gpu"] = ref_gpu_leg(dev, batch, line["ms_per_step"])
     if rank == 0 and not args.no_model:
         try:
             line["fusion_blocks"] = fusion_leg(dev, line["clocks"].get("sm_mhz") or 1965)
@@ -477,6 +506,7 @@ def main():
     ap.add_argument("--workload", default="ss2d", help="ss2d (default, BASELINE config 2) or xfmamba_{t,s,b}_infer / "
                     "xfmamba_{s,b}_train / xfmamba_b_hires (end-to-end model, configs 3-5; see bench_model.py)")
     ap.add_argument("--no-graph", action="store_true", help="model inference workloads: eager instead of a CUDA graph")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the ref_gpu leg (the reference's CUDA scan on the same box)")
     ap.add_argument("--no-model", action="store_true", help="skip the model_train leg (XFMamba-B training step, config 4)")
     ap.add_argument("--model-batch", type=int, default=32, help="pairs per GPU of the model_train leg")
     ap.add_argument("--model-steps", type=int, default=8, help="timed steps of the model_train leg")

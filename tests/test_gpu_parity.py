@@ -813,3 +813,31 @@ def test_ss2d_bwd_accumulator_replicas_agree(xf, shape):
         assert got[3].shape == base[3].shape
         for a, b in zip(got, base):
             assert rel_err(a, b) < 1e-5
+
+
+# ---- the reference's own CUDA kernel on the same box (oracle/_ref, built from /root/reference by oracle/build_ref.py) ----
+@pytest.mark.parametrize("B,D,H,W", [(4, 48, 56, 56), (2, 24, 28, 28), (3, 16, 14, 14), (2, 8, 20, 19)])
+def test_ss2d_vs_reference_cuda_core(B, D, H, W):
+    """fused SS2D core fwd + bwd against selective_scan_cuda_core.fwd / .bwd (models/csms6s.py:83, 101) between torch
+    CrossScan / CrossMerge (models/csm_triton.py:22-30, 56-62): both fp32 on the GPU, fast-math on both sides"""
+    from oracle import ref_gpu
+    if not ref_gpu.available():
+        pytest.skip("oracle/_ref/selective_scan_cuda_core.so not built")
+    from xfmamba_b200 import ss2d_scan
+    m = ref_gpu.load()
+    torch.manual_seed(B * 100 + H)
+    L, KD = H * W, 4 * D
+    x = torch.randn(B, D, H, W, device=dev())
+    delta = 0.5 * torch.rand(B, KD, L, device=dev())
+    A = -0.5 * torch.rand(KD, 1, device=dev())
+    Bs, Cs = torch.randn(B, 4, 1, L, device=dev()), torch.randn(B, 4, 1, L, device=dev())
+    Ds, bias = torch.randn(KD, device=dev()), 0.5 * torch.rand(KD, device=dev())
+    dy = torch.randn(B, D, L, device=dev())
+    y_ref, saved = ref_gpu.ss2d_fwd(m, x, delta, A, Bs, Cs, Ds, bias)
+    g_ref = ref_gpu.ss2d_bwd(m, saved, dy, x.shape, delta, A, Bs, Cs, Ds, bias)
+    leaves = [t_.clone().requires_grad_() for t_ in (x, delta, A, Bs, Cs, Ds, bias)]
+    y = ss2d_scan(*leaves, True, True)
+    g = torch.autograd.grad(y, leaves, dy)
+    assert rel_err(n(y), n(y_ref)) < TOL32
+    for name, a, b in zip(("dx", "ddelta", "dA", "dBs", "dCs", "dDs", "ddelta_bias"), g, g_ref):
+        assert rel_err(n(a).reshape(-1), n(b).reshape(-1)) < TOL32, name

@@ -7,10 +7,11 @@
 // into the scan kernel instead; with one channel per CTA (what the four shared-memory image buffers allow) every CTA would
 // re-read all R rows of z, i.e. R times the L2 traffic of delta itself, so the projection stays a separate, write-bound pass.
 //
-// fp32 FMA on purpose: TF32 tensor cores would miss the 1e-4 parity bar on delta.
+// Two kernels: an fp32 FFMA2 kernel (first) and a 3xTF32 warp-MMA kernel (second, the default); plain TF32 would miss the 1e-4 parity bar.
 // CTA = one (b, k), NCG groups of 8 channels x PG groups of 4 positions; z tile [R][4*PG] and W tile [R][8*NCG] in shared
 // memory; a thread owns 8 channels x 4 positions (packed FFMA2 over position pairs), items flattened so that short rows
 // (L = 196, 49) still fill the CTA.  The backward (dz = W^T g, dW = sum_b g z^T) is two plain batched GEMMs and goes to cuBLAS from proj.py.
+#include <cstdlib>
 #include "xfscan_common.cuh"
 
 namespace xfs {
@@ -124,6 +125,192 @@ dtproj_fwd_kernel(const T* __restrict__ z, const float* __restrict__ W, T* __res
     }
 }
 
+// ---- forward on the tensor pipe: 3xTF32 ---------------------------------------------------------------------------------
+// The FFMA2 kernel above is bound by shared-memory operand traffic (ncu: LSU wavefronts 86 %, FMA pipe 66 %) at 1.8-2.8 TB/s of
+// delta for the 28x28 / 14x14 stages.  The contraction is a batched (D x R) x (R x L) product with R <= 64, so the legacy warp
+// MMA (mma.sync m16n8k8, tf32 in / fp32 accumulate) does it with 1/6 of the operand loads; fp32 accuracy is kept by splitting both
+// operands into a tf32 head and a tf32 tail (x = hi + lo, 21 significant bits; z at staging time, W at use) and issuing three MMAs per tile,
+// lo*hi + hi*lo + hi*hi (the dropped lo*lo term is 2^-22 relative).  tcgen05 is not used: K = R is 8..64, the tiles are tiny and
+// the kernel only has to stay under the time it takes to write delta.
+// CTA = 8 warps, (k, NB images, 16*4*kMW channels, <= 256 positions); warp w owns kMW m-tiles (16 channels each) and sweeps the
+// n-tiles (8 positions) in groups of 4, even groups for warps 0-3 and odd groups for warps 4-7.  W is staged in fragment order (one LDS.128 per m-tile and k-step), z as [r][column] hi / lo
+// planes with a row pitch = 8 mod 32 words so that the B-fragment loads are conflict free.
+constexpr int kMmaThreads = 256;
+constexpr int kMmaG = 4;             // n-tiles per accumulator group
+constexpr int kMmaTP = 40;           // row pitch (floats) of a warp's transposition tile: conflict free both ways
+
+struct DtMma {
+    int D, R, L, K, B;
+    int kK;                          // k-steps of 8 ranks (R padded with zeros)
+    int NT, NTpad, NB, cols, pitch;  // positions per image and CTA, padded to 8; images per CTA; columns = NB * NTpad
+    int64_t z_sb, z_sk;
+    bool vec4, vec2;                 // 16-byte z loads / 4-position delta stores allowed
+};
+
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
+    hi = __uint_as_float(tf32_rna(x));
+    lo = __uint_as_float(tf32_rna(x - hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint4& a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+
+template <typename T, int kMW>
+__global__ void __launch_bounds__(kMmaThreads, 3)
+dtproj_mma_fwd_kernel(const T* __restrict__ z, const float* __restrict__ W, T* __restrict__ out, const DtMma g) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int kMT = 4 * kMW;                                  // m-tiles per CTA
+    float* sA = smem;                                             // [kMT][kK][32 lanes] float4, fragment order (fp32; split at use)
+    float* sBh = sA + kMT * g.kK * 32 * 4;                        // [8 * kK][pitch]
+    float* sBl = sBh + 8 * g.kK * g.pitch;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q = lane >> 2, t4 = lane & 3;
+    const int bgk = blockIdx.z, bg = bgk / g.K, k = bgk - bg * g.K;
+    const int b0 = bg * g.NB, l0 = blockIdx.x * g.NT, d0 = blockIdx.y * (16 * kMT);
+    const int R8 = 8 * g.kK;
+
+    // W tile (fp32), one item per fragment slot: a0 (row q, col t4), a1 (q + 8, t4), a2 (q, t4 + 4), a3 (q + 8, t4 + 4)
+    for (int i = tid; i < kMT * g.kK * 32; i += kMmaThreads) {
+        const int mk = i >> 5, mt = mk / g.kK, ks = mk - mt * g.kK;
+        const int d = d0 + mt * 16 + q, r = ks * 8 + t4;          // lane of the slot = this thread's lane (kMmaThreads % 32 == 0)
+        const float* __restrict__ wr = W + ((int64_t)k * g.D + d) * g.R + r;
+        const bool d_lo = d < g.D, d_hi = d + 8 < g.D, r_lo = r < g.R, r_hi = r + 4 < g.R;
+        const float a0 = (d_lo && r_lo) ? __ldg(wr) : 0.0f, a1 = (d_hi && r_lo) ? __ldg(wr + 8 * g.R) : 0.0f;
+        const float a2 = (d_lo && r_hi) ? __ldg(wr + 4) : 0.0f, a3 = (d_hi && r_hi) ? __ldg(wr + 8 * g.R + 4) : 0.0f;
+        reinterpret_cast<float4*>(sA)[mk * 32 + lane] = make_float4(a0, a1, a2, a3);
+    }
+    // z tile -> [r][column] head / tail planes (warps stride the rows, lanes the columns); rows R..R8 and columns past the row end are zero
+    const T* __restrict__ zk = z + (int64_t)k * g.z_sk + (int64_t)b0 * g.z_sb;
+    if (g.vec4) {
+        const int c4 = g.cols >> 2, n4 = g.NTpad >> 2;
+        for (int r = warp; r < R8; r += kMmaThreads / 32)
+            for (int c = lane; c < c4; c += 32) {
+                const int bl = g.NB > 1 ? c / n4 : 0, l = l0 + 4 * (c - bl * n4);
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                if (r < g.R && l < g.L && b0 + bl < g.B) {
+                    const T* __restrict__ src = zk + (int64_t)bl * g.z_sb + (int64_t)r * g.L + l;
+                    if constexpr (sizeof(T) == 4) {
+                        const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+                        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+                    } else {
+                        const uint2 a = __ldg(reinterpret_cast<const uint2*>(src));
+                        const T* e = reinterpret_cast<const T*>(&a);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[j] = Elem<T>::to_f(e[j]);
+                    }
+                }
+                float4 h, t;
+                tf32_split(v[0], h.x, t.x); tf32_split(v[1], h.y, t.y); tf32_split(v[2], h.z, t.z); tf32_split(v[3], h.w, t.w);
+                *reinterpret_cast<float4*>(sBh + r * g.pitch + 4 * c) = h;
+                *reinterpret_cast<float4*>(sBl + r * g.pitch + 4 * c) = t;
+            }
+    } else {
+        for (int r = warp; r < R8; r += kMmaThreads / 32)
+            for (int c = lane; c < g.cols; c += 32) {
+                const int bl = g.NB > 1 ? c / g.NTpad : 0, p = c - bl * g.NTpad, l = l0 + p;
+                float v = 0.0f;
+                if (r < g.R && l < g.L && p < g.NT && b0 + bl < g.B) v = Elem<T>::to_f(zk[(int64_t)bl * g.z_sb + (int64_t)r * g.L + l]);
+                float h, t;
+                tf32_split(v, h, t);
+                sBh[r * g.pitch + c] = h;
+                sBl[r * g.pitch + c] = t;
+            }
+    }
+    __syncthreads();
+
+    // warp w: m-tiles (w & 3) * kMW .., n-tile groups of parity w >> 2
+    const int mw0 = (warp & 3) * kMW;
+    const int ntiles = g.cols >> 3;
+    const float4* __restrict__ aw = reinterpret_cast<const float4*>(sA) + (mw0 * g.kK) * 32 + lane;
+    float* st = sBl + 8 * g.kK * g.pitch + warp * (16 * kMmaTP);   // this warp's 16 x 32 transposition tile
+    const int seg = lane & 7, srow = lane >> 3;
+    for (int n0 = (warp >> 2) * kMmaG; n0 < ntiles; n0 += 2 * kMmaG) {
+        float acc[kMW][kMmaG][4];
+#pragma unroll
+        for (int m = 0; m < kMW; ++m)
+#pragma unroll
+            for (int j = 0; j < kMmaG; ++j)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[m][j][e] = 0.0f;
+        const uint32_t* __restrict__ bh = reinterpret_cast<const uint32_t*>(sBh) + t4 * g.pitch + n0 * 8 + q;
+        const uint32_t* __restrict__ bt = reinterpret_cast<const uint32_t*>(sBl) + t4 * g.pitch + n0 * 8 + q;
+        const int nv = ntiles - n0;                               // valid tiles of this group (>= 1)
+        for (int ks = 0; ks < g.kK; ++ks) {
+            uint4 ah[kMW], al[kMW];
+#pragma unroll
+            for (int m = 0; m < kMW; ++m) {
+                const float4 a = aw[(m * g.kK + ks) * 32];
+                float4 hi, lo;
+                tf32_split(a.x, hi.x, lo.x); tf32_split(a.y, hi.y, lo.y); tf32_split(a.z, hi.z, lo.z); tf32_split(a.w, hi.w, lo.w);
+                ah[m] = make_uint4(__float_as_uint(hi.x), __float_as_uint(hi.y), __float_as_uint(hi.z), __float_as_uint(hi.w));
+                al[m] = make_uint4(__float_as_uint(lo.x), __float_as_uint(lo.y), __float_as_uint(lo.z), __float_as_uint(lo.w));
+            }
+            uint32_t h0[kMmaG], h1[kMmaG], t0[kMmaG], t1[kMmaG];
+            const int ro = ks * 8 * g.pitch;
+#pragma unroll
+            for (int j = 0; j < kMmaG; ++j) {
+                const int cj = j < nv ? 8 * j : 0;               // the tail group re-reads tile 0 (results discarded)
+                h0[j] = bh[ro + cj]; h1[j] = bh[ro + 4 * g.pitch + cj];
+                t0[j] = bt[ro + cj]; t1[j] = bt[ro + 4 * g.pitch + cj];
+            }
+            // three passes over independent accumulators: small terms first
+#pragma unroll
+            for (int j = 0; j < kMmaG; ++j)
+#pragma unroll
+                for (int m = 0; m < kMW; ++m) mma_tf32(acc[m][j], al[m], h0[j], h1[j]);
+#pragma unroll
+            for (int j = 0; j < kMmaG; ++j)
+#pragma unroll
+                for (int m = 0; m < kMW; ++m) mma_tf32(acc[m][j], ah[m], t0[j], t1[j]);
+#pragma unroll
+            for (int j = 0; j < kMmaG; ++j)
+#pragma unroll
+                for (int m = 0; m < kMW; ++m) mma_tf32(acc[m][j], ah[m], h0[j], h1[j]);
+        }
+        // accumulators (c0, c1: row q, columns 2 t4, 2 t4 + 1; c2, c3: row q + 8) -> shared tile -> full 128-byte row segments
+        const int cc = n0 * 8 + 4 * seg;                          // this lane's 4 columns of the group
+        const int bl = g.NB > 1 ? cc / g.NTpad : 0, pp = cc - bl * g.NTpad, l = l0 + pp;
+        const bool colok = cc < g.cols && pp < g.NT && l < g.L && b0 + bl < g.B;
+        T* __restrict__ obase = out + (((int64_t)(b0 + bl) * g.K + k) * g.D + d0 + mw0 * 16) * g.L + l;
+#pragma unroll
+        for (int m = 0; m < kMW; ++m) {
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < kMmaG; ++j) {
+                *reinterpret_cast<float2*>(st + q * kMmaTP + 8 * j + 2 * t4) = make_float2(acc[m][j][0], acc[m][j][1]);
+                *reinterpret_cast<float2*>(st + (q + 8) * kMmaTP + 8 * j + 2 * t4) = make_float2(acc[m][j][2], acc[m][j][3]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int row = m * 16 + srow + 4 * it;
+                if (!colok || d0 + mw0 * 16 + row >= g.D) continue;
+                const float4 v = *reinterpret_cast<const float4*>(st + (srow + 4 * it) * kMmaTP + 4 * seg);
+                T* __restrict__ o = obase + (int64_t)row * g.L;
+                if (g.vec2) {                                     // rows are 16-byte (8-byte for 16-bit types) aligned
+                    if constexpr (sizeof(T) == 4) *reinterpret_cast<float4*>(o) = v;
+                    else {
+                        T e[4] = {Elem<T>::from_f(v.x), Elem<T>::from_f(v.y), Elem<T>::from_f(v.z), Elem<T>::from_f(v.w)};
+                        *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(e);
+                    }
+                } else {
+                    const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (l + c < g.L) o[c] = Elem<T>::from_f(e[c]);
+                }
+            }
+        }
+    }
+}
+
 static DtGeom dt_geom(int64_t B, int64_t D, int64_t R, int64_t L, int64_t K, int64_t z_sb, int64_t z_sk, bool aligned) {
     DtGeom g;
     g.D = (int)D; g.R = (int)R; g.L = (int)L; g.K = (int)K; g.B = (int)B;
@@ -157,9 +344,63 @@ static DtGeom dt_geom(int64_t B, int64_t D, int64_t R, int64_t L, int64_t K, int
     return g;
 }
 
+static size_t dt_mma_smem(const DtMma& g, int mw) {
+    return sizeof(float) * ((size_t)4 * mw * g.kK * 32 * 4 + (size_t)2 * 8 * g.kK * g.pitch + (size_t)(kMmaThreads / 32) * 16 * kMmaTP);
+}
+
+static int launch_dtproj_mma(const void* z, const float* W, void* out, int64_t B, int64_t K, int64_t D, int64_t R, int64_t L, int64_t z_sb,
+                             int64_t z_sk, int dtype, cudaStream_t st) {
+    DtMma g;
+    g.D = (int)D; g.R = (int)R; g.L = (int)L; g.K = (int)K; g.B = (int)B;
+    g.kK = (int)((R + 7) / 8);
+    const int mw = (D % 128 == 0 || D >= 512) ? 2 : 1;             // 128 channels per CTA unless that leaves a half-empty block
+    // columns per CTA: at most 256, fewer for large ranks so that two CTAs still fit an SM (~100 KB each)
+    const int budget = (54 * 1024 - 2 * mw * g.kK * 1024) / (64 * g.kK);         // 3 CTAs per SM: ~74 KB each incl. the 20 KB of transposition tiles
+    int maxcols = budget < 256 ? (budget / 8) * 8 : 256;
+    if (maxcols < 32) maxcols = 32;
+    const int L8 = (int)((L + 7) / 8) * 8;
+    unsigned ltiles = 1;
+    if (L8 <= maxcols) {                                            // whole rows: several images per CTA share the weight tile
+        g.NT = (int)L; g.NTpad = L8;
+        g.NB = maxcols / L8;
+        if (g.NB > B) g.NB = (int)B;
+        if (g.NB > 8) g.NB = 8;
+    } else {
+        ltiles = (unsigned)((L + maxcols - 1) / maxcols);
+        g.NT = (int)(((L + ltiles - 1) / ltiles + 7) / 8) * 8;
+        g.NTpad = g.NT;
+        g.NB = 1;
+        ltiles = (unsigned)((L + g.NT - 1) / g.NT);
+    }
+    g.cols = g.NB * g.NTpad;
+    g.pitch = g.cols + ((8 - g.cols % 32) + 32) % 32;               // = 8 (mod 32)
+    g.z_sb = z_sb; g.z_sk = z_sk;
+    const int esz = dtype == XFS_F32 ? 4 : 2;
+    g.vec4 = (reinterpret_cast<uintptr_t>(z) % (4 * esz) == 0) && (L % 4 == 0) && (z_sb % 4 == 0) && (z_sk % 4 == 0);
+    g.vec2 = (reinterpret_cast<uintptr_t>(out) % (4 * esz) == 0) && (L % 4 == 0);
+    const dim3 grid(ltiles, (unsigned)((D + 64 * mw - 1) / (64 * mw)), (unsigned)(((B + g.NB - 1) / g.NB) * K));
+    if (grid.y > 65535 || grid.z > 65535) return XFS_ERR_SHAPE;
+    const size_t smem = dt_mma_smem(g, mw);
+#define XFS_DT_MMA(T, M)                                                                                                \
+    do {                                                                                                                \
+        cudaFuncSetAttribute(dtproj_mma_fwd_kernel<T, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+        dtproj_mma_fwd_kernel<T, M><<<grid, kMmaThreads, smem, st>>>((const T*)z, W, (T*)out, g);                        \
+    } while (0)
+    if (dtype == XFS_F32) { if (mw == 2) XFS_DT_MMA(float, 2); else XFS_DT_MMA(float, 1); }
+    else if (dtype == XFS_BF16) { if (mw == 2) XFS_DT_MMA(__nv_bfloat16, 2); else XFS_DT_MMA(__nv_bfloat16, 1); }
+    else { if (mw == 2) XFS_DT_MMA(__half, 2); else XFS_DT_MMA(__half, 1); }
+#undef XFS_DT_MMA
+    return check_launch();
+}
+
 int launch_dtproj_fwd(const void* z, const float* W, void* out, int64_t B, int64_t K, int64_t D, int64_t R, int64_t L, int64_t z_sb,
                       int64_t z_sk, int dtype, cudaStream_t st) {
     if (R > kDtMaxRank) return XFS_ERR_UNSUPPORTED;
+    // tensor-pipe kernel except for one k-step with 64-channel CTAs (R <= 8 and D not a multiple of 128: the T/S stage-1 shape), where the
+    // FFMA2 kernel below is already at 4.9 TB/s of delta and the MMA kernel reaches 3.8 (B200, profiles/r02_ops_sweep.md)
+    static const bool force_fma = getenv("XFS_DTPROJ_FMA") != nullptr;    // timing experiments
+    const bool one_step_narrow = R <= 8 && !(D % 128 == 0 || D >= 512);
+    if (!force_fma && !one_step_narrow) return launch_dtproj_mma(z, W, out, B, K, D, R, L, z_sb, z_sk, dtype, st);
     const int esz = dtype == XFS_F32 ? 4 : 2;
     const bool aligned = ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(out)) % (4 * esz)) == 0;
     const DtGeom g = dt_geom(B, D, R, L, K, z_sb, z_sk, aligned);
