@@ -841,3 +841,38 @@ def test_ss2d_vs_reference_cuda_core(B, D, H, W):
     assert rel_err(n(y), n(y_ref)) < TOL32
     for name, a, b in zip(("dx", "ddelta", "dA", "dBs", "dCs", "dDs", "ddelta_bias"), g, g_ref):
         assert rel_err(n(a).reshape(-1), n(b).reshape(-1)) < TOL32, name
+
+
+@pytest.mark.parametrize("B,K,C,N,L,dtype,softplus", [
+    (2, 2, 96, 16, 49, "f32", True),        # the 7x7 fusion blocks: K = 2 (swap scan), N = 16
+    (2, 4, 24, 1, 3136, "f32", True),       # stage-1 rows, N = 1 (the d_state = 1 kernels)
+    (1, 4, 8, 4, 1500, "f32", False),       # no softplus, L crossing chunk boundaries, N = 4
+    (2, 4, 16, 1, 784, "bf16", True),
+    (2, 2, 32, 16, 49, "f16", True),
+])
+def test_selective_scan_fn_vs_reference_cuda_core(B, K, C, N, L, dtype, softplus):
+    """stand-alone selective_scan_fn fwd + all 7 gradients against the reference's kernel (models/csms6s.py:83, 101)"""
+    from oracle import ref_gpu
+    if not ref_gpu.available():
+        pytest.skip("oracle/_ref/selective_scan_cuda_core.so not built")
+    from xfmamba_b200 import csms6s
+    m = ref_gpu.load()
+    torch.manual_seed(L + N)
+    tdt = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}[dtype]
+    tol = TOL32 if dtype == "f32" else TOL16
+    KD = K * C
+    u = torch.randn(B, KD, L, device=dev()).to(tdt)
+    delta = (0.5 * torch.rand(B, KD, L, device=dev())).to(tdt)
+    A = -0.5 * torch.rand(KD, N, device=dev())
+    Bs, Cs = torch.randn(B, K, N, L, device=dev()).to(tdt), torch.randn(B, K, N, L, device=dev()).to(tdt)
+    Ds, bias = torch.randn(KD, device=dev()), 0.5 * torch.rand(KD, device=dev())
+    dy = torch.randn(B, KD, L, device=dev()).to(tdt)
+    out, st, *_ = m.fwd(u, delta, A, Bs, Cs, Ds, bias, softplus, 1)
+    g_ref = m.bwd(u, delta, A, Bs, Cs, Ds, bias, dy, st, softplus, 1)[:7]
+    leaves = [t_.clone().requires_grad_() for t_ in (u, delta, A, Bs, Cs, Ds, bias)]
+    y = csms6s.selective_scan_fn(*leaves, softplus, False)          # oflex=False: output in the input dtype, as the core backend
+    assert y.dtype == out.dtype
+    g = torch.autograd.grad(y, leaves, dy)
+    assert rel_err(n(y.float()), n(out.float())) < tol
+    for name, a, b in zip(("du", "ddelta", "dA", "dB", "dC", "dD", "ddelta_bias"), g, g_ref):
+        assert rel_err(n(a.float()).reshape(-1), n(b.float()).reshape(-1)) < tol, name
