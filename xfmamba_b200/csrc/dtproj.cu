@@ -176,6 +176,22 @@ dtproj_mma_fwd_kernel(const T* __restrict__ z, const float* __restrict__ W, T* _
     const int b0 = bg * g.NB, l0 = blockIdx.x * g.NT, d0 = blockIdx.y * (16 * kMT);
     const int R8 = 8 * g.kK;
 
+    const T* __restrict__ zk = z + (int64_t)k * g.z_sk + (int64_t)b0 * g.z_sb;
+    const bool async_z = sizeof(T) == 4 && g.vec4;
+    if (async_z) {
+        // fp32 z tile: every thread puts all its 16-byte pieces in flight at once (cp.async, zero fill where out of range) and splits
+        // them in place below, after the W tile -- one load latency per CTA instead of one per loop trip
+        const int c4 = g.cols >> 2, n4 = g.NTpad >> 2;
+        for (int r = warp; r < R8; r += kMmaThreads / 32)
+            for (int c = lane; c < c4; c += 32) {
+                const int bl = g.NB > 1 ? c / n4 : 0, l = l0 + 4 * (c - bl * n4);
+                const bool in = r < g.R && l < g.L && b0 + bl < g.B;
+                const T* __restrict__ src = in ? zk + (int64_t)bl * g.z_sb + (int64_t)r * g.L + l : zk;
+                const uint32_t sa = (uint32_t)__cvta_generic_to_shared(sBh + r * g.pitch + 4 * c);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(src), "r"(in ? 16 : 0));
+            }
+        asm volatile("cp.async.commit_group;" ::);
+    }
     // W tile (fp32), one item per fragment slot: a0 (row q, col t4), a1 (q + 8, t4), a2 (q, t4 + 4), a3 (q + 8, t4 + 4)
     for (int i = tid; i < kMT * g.kK * 32; i += kMmaThreads) {
         const int mk = i >> 5, mt = mk / g.kK, ks = mk - mt * g.kK;
@@ -187,8 +203,18 @@ dtproj_mma_fwd_kernel(const T* __restrict__ z, const float* __restrict__ W, T* _
         reinterpret_cast<float4*>(sA)[mk * 32 + lane] = make_float4(a0, a1, a2, a3);
     }
     // z tile -> [r][column] head / tail planes (warps stride the rows, lanes the columns); rows R..R8 and columns past the row end are zero
-    const T* __restrict__ zk = z + (int64_t)k * g.z_sk + (int64_t)b0 * g.z_sb;
-    if (g.vec4) {
+    if (async_z) {
+        const int c4 = g.cols >> 2;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        for (int r = warp; r < R8; r += kMmaThreads / 32)
+            for (int c = lane; c < c4; c += 32) {
+                const float4 v = *reinterpret_cast<const float4*>(sBh + r * g.pitch + 4 * c);
+                float4 h, t;
+                tf32_split(v.x, h.x, t.x); tf32_split(v.y, h.y, t.y); tf32_split(v.z, h.z, t.z); tf32_split(v.w, h.w, t.w);
+                *reinterpret_cast<float4*>(sBh + r * g.pitch + 4 * c) = h;
+                *reinterpret_cast<float4*>(sBl + r * g.pitch + 4 * c) = t;
+            }
+    } else if (g.vec4) {
         const int c4 = g.cols >> 2, n4 = g.NTpad >> 2;
         for (int r = warp; r < R8; r += kMmaThreads / 32)
             for (int c = lane; c < c4; c += 32) {
