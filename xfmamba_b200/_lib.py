@@ -91,7 +91,7 @@ SYMBOLS = [
     "xfs_cross_scan", "xfs_cross_merge", "xfs_swap_scan", "xfs_swap_merge", "xfs_swap_stack",
     "xfs_selective_scan_fwd", "xfs_selective_scan_bwd", "xfs_ss2d_supported", "xfs_ss2d_states_len", "xfs_ss2d_fwd", "xfs_ss2d_bwd",
     "xfs_layernorm2d_fwd", "xfs_layernorm2d_bwd",
-    "xfs_dwconv3x3_supported", "xfs_dwconv3x3_fwd", "xfs_dwconv3x3_bwd", "xfs_dt_proj_fwd",
+    "xfs_dwconv3x3_supported", "xfs_dwconv3x3_fwd", "xfs_dwconv3x3_bwd", "xfs_dt_proj_fwd", "xfs_dt_proj_bwd", "xfs_dt_proj_bwd_supported",
     "xfs_cross_ss2d_x3_supported", "xfs_cross_ss2d_x3_fwd", "xfs_cross_ss2d_x3_bwd",
     "xfs_swap_scan_fused_supported", "xfs_swap_scan_fused_fwd", "xfs_swap_scan_fused_bwd",
 ]
@@ -137,6 +137,8 @@ def lib() -> ctypes.CDLL:
     L.xfs_dwconv3x3_fwd.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, ctypes.c_int, ctypes.c_int, c_vp]
     L.xfs_dwconv3x3_bwd.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, ctypes.c_int, ctypes.c_int, c_vp]
     L.xfs_dt_proj_fwd.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, ctypes.c_int, c_vp]
+    L.xfs_dt_proj_bwd.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, c_i64, ctypes.c_int, c_vp]
+    L.xfs_dt_proj_bwd_supported.argtypes = [c_i64, c_i64, c_i64, c_i64, ctypes.c_int]
     L.xfs_cross_ss2d_x3_supported.argtypes = [c_i64, c_i64, c_i64]
     L.xfs_cross_ss2d_x3_fwd.argtypes = [ctypes.POINTER(X3FwdArgs), c_vp]
     L.xfs_cross_ss2d_x3_bwd.argtypes = [ctypes.POINTER(X3BwdArgs), c_vp]

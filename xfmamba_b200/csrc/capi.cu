@@ -43,6 +43,7 @@ int launch_dwconv_fwd(const void*, const float*, const float*, void*, int64_t, i
 int launch_dwconv_bwd(const void*, const float*, const float*, const void*, void*, float*, int64_t, int64_t, int64_t, int64_t, int, int, cudaStream_t);
 
 int launch_dtproj_fwd(const void*, const float*, void*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int, cudaStream_t);
+int launch_dtproj_bwd(const float*, const float*, const float*, float*, float*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, cudaStream_t);
 
 static std::atomic<long long> g_launches{0};
 
@@ -287,6 +288,19 @@ int xfs_dt_proj_fwd(const void* z, const float* W, void* delta, int64_t B, int64
     if (B <= 0 || K <= 0 || D <= 0 || R <= 0 || L <= 0 || z_batch_stride < 0 || z_route_stride < 0) return XFS_ERR_SHAPE;
     if (bad_dtype(dtype)) return XFS_ERR_DTYPE;
     return launch_dtproj_fwd(z, W, delta, B, K, D, R, L, z_batch_stride, z_route_stride, dtype, (cudaStream_t)stream);
+}
+
+int xfs_dt_proj_bwd_supported(int64_t R, int64_t L, int64_t z_batch_stride, int64_t z_route_stride, int dtype) {
+    return dtype == XFS_F32 && R > 0 && R <= 64 && L > 0 && L % 4 == 0 && z_batch_stride % 4 == 0 && z_route_stride % 4 == 0;
+}
+
+int xfs_dt_proj_bwd(const void* g, const void* z, const float* W, void* dz, float* dW, int64_t B, int64_t K, int64_t D, int64_t R, int64_t L,
+                    int64_t z_batch_stride, int64_t z_route_stride, int dtype, xfs_stream_t stream) {
+    if (!g || !z || !W || (!dz && !dW)) return XFS_ERR_NULL;
+    if (B <= 0 || K <= 0 || D <= 0 || R <= 0 || L <= 0 || z_batch_stride < 0 || z_route_stride < 0) return XFS_ERR_SHAPE;
+    if (bad_dtype(dtype)) return XFS_ERR_DTYPE;
+    if (!xfs_dt_proj_bwd_supported(R, L, z_batch_stride, z_route_stride, dtype)) return XFS_ERR_UNSUPPORTED;
+    return launch_dtproj_bwd((const float*)g, (const float*)z, W, (float*)dz, dW, B, K, D, R, L, z_batch_stride, z_route_stride, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -447,4 +447,254 @@ int launch_dtproj_fwd(const void* z, const float* W, void* out, int64_t B, int64
     return check_launch();
 }
 
+// ---- backward on the tensor pipe (fp32 rows, L % 4 == 0): dz = W^T g and dW = sum_{b,l} g z^T, one pass over g each -----------------
+// cuBLAS ran these as two batched SIMT sgemms (matmul does not use TF32) plus a reduction over the batch: 274 us per 14x14 block
+// of XFMamba-B (B = 64, R = 32, D = 1024) against 31 us for reading g once.  Same 3xTF32 arithmetic as the forward; the g tiles are
+// streamed with cp.async (16-byte pieces, zero fill out of range) through a two-slot ring, the small operand is split at staging or at use.
+constexpr int kBwThreads = 256;
+constexpr int kDzKC = 32;            // dz: d rows of g per ring slot (4 k-steps)
+constexpr int kDwLC = 32;            // dW: columns of g / z per ring slot (4 k-steps)
+constexpr int kDwPitch = 36;         //   = 4 (mod 32): conflict-free A and B fragments
+constexpr int kDwMT = 128;           // dW: d rows per CTA (one m-tile per warp)
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool in) {
+    const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gsrc), "r"(in ? 16 : 0));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
+template <int kN>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kN) : "memory"); }
+
+// dz[b, k, r, l] = sum_d W[k, d, r] g[b, k, d, l]: M = r (kRT m-tiles of 16), N = l, K = d.  CTA = (b, k, NT <= 256 columns); warp w owns
+// n-tiles w, w + 8, ... (kNW of them), so one W^T chunk (staged once per CTA and 32 d rows, head / tail split there) serves up to 32 n-tiles.
+template <int kRT, int kNW>
+__global__ void __launch_bounds__(kBwThreads)
+dtproj_dz_kernel(const float* __restrict__ g, const float* __restrict__ W, float* __restrict__ dz, int D, int R, int L, int K, int NT,
+                 int pitch) {
+    extern __shared__ __align__(16) float smem[];
+    float* sA = smem;                                          // [m-tile][k-step][hi, lo][lane] float4, fragment order
+    float* sG = smem + kRT * (kDzKC / 8) * 2 * 32 * 4;         // [2 slots][32 d rows][pitch], pitch = 8 (mod 32)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = lane >> 2, t4 = lane & 3;
+    const int bk = blockIdx.y, k = bk % K, l0 = blockIdx.x * NT;
+    const float* __restrict__ gb = g + (int64_t)bk * D * L;
+    const float* __restrict__ Wk = W + (int64_t)k * D * R;
+    const int nchunks = (D + kDzKC - 1) / kDzKC, p4 = NT >> 2, ntiles = NT >> 3;
+    auto issue = [&](int c) {
+        float* dst = sG + (c & 1) * kDzKC * pitch;
+        for (int r = warp; r < kDzKC; r += kBwThreads / 32) {
+            const int d = c * kDzKC + r;
+            for (int c4 = lane; c4 < p4; c4 += 32) {
+                const int l = l0 + 4 * c4;
+                const bool in = d < D && l < L;
+                cp_async16_zfill(dst + r * pitch + 4 * c4, in ? gb + (int64_t)d * L + l : gb, in);
+            }
+        }
+        cp_async_commit();
+    };
+    float acc[kRT][kNW][4];
+#pragma unroll
+    for (int m = 0; m < kRT; ++m)
+#pragma unroll
+        for (int j = 0; j < kNW; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[m][j][e] = 0.0f;
+    issue(0);
+    for (int c = 0; c < nchunks; ++c) {
+        if (c + 1 < nchunks) issue(c + 1);
+        // W^T chunk in A-fragment order: a0 (r = q, d = t4), a1 (q + 8, t4), a2 (q, t4 + 4), a3 (q + 8, t4 + 4)
+        for (int i = tid; i < kRT * (kDzKC / 8) * 32; i += kBwThreads) {
+            const int mk = i >> 5, mt = mk / (kDzKC / 8), ks = mk - mt * (kDzKC / 8);
+            const int r = mt * 16 + q, d = c * kDzKC + ks * 8 + t4;
+            const float* __restrict__ wp = Wk + (int64_t)d * R + r;
+            const bool r0 = r < R, r1 = r + 8 < R, d0 = d < D, d1 = d + 4 < D;
+            const float a0 = (r0 && d0) ? __ldg(wp) : 0.0f, a1 = (r1 && d0) ? __ldg(wp + 8) : 0.0f;
+            const float a2 = (r0 && d1) ? __ldg(wp + 4 * R) : 0.0f, a3 = (r1 && d1) ? __ldg(wp + 4 * R + 8) : 0.0f;
+            float4 hi, lo;
+            tf32_split(a0, hi.x, lo.x); tf32_split(a1, hi.y, lo.y); tf32_split(a2, hi.z, lo.z); tf32_split(a3, hi.w, lo.w);
+            float4* dst = reinterpret_cast<float4*>(sA) + (mk * 2) * 32 + lane;
+            dst[0] = hi;
+            dst[32] = lo;
+        }
+        if (c + 1 < nchunks) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncthreads();
+        const float* __restrict__ gt = sG + (c & 1) * kDzKC * pitch + t4 * pitch + q;
+        const uint4* __restrict__ aw = reinterpret_cast<const uint4*>(sA) + lane;
+#pragma unroll
+        for (int ks = 0; ks < kDzKC / 8; ++ks) {
+            uint4 ah[kRT], al[kRT];
+#pragma unroll
+            for (int m = 0; m < kRT; ++m) {
+                ah[m] = aw[((m * (kDzKC / 8) + ks) * 2) * 32];
+                al[m] = aw[((m * (kDzKC / 8) + ks) * 2 + 1) * 32];
+            }
+            float h0[kNW], h1[kNW], t0[kNW], t1[kNW];
+#pragma unroll
+            for (int j = 0; j < kNW; ++j) {
+                const int nt = warp + 8 * j, col = nt < ntiles ? nt * 8 : 0;     // tail tiles re-read tile 0, results discarded
+                tf32_split(gt[ks * 8 * pitch + col], h0[j], t0[j]);
+                tf32_split(gt[(ks * 8 + 4) * pitch + col], h1[j], t1[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < kNW; ++j)
+#pragma unroll
+                for (int m = 0; m < kRT; ++m) mma_tf32(acc[m][j], al[m], __float_as_uint(h0[j]), __float_as_uint(h1[j]));
+#pragma unroll
+            for (int j = 0; j < kNW; ++j)
+#pragma unroll
+                for (int m = 0; m < kRT; ++m) mma_tf32(acc[m][j], ah[m], __float_as_uint(t0[j]), __float_as_uint(t1[j]));
+#pragma unroll
+            for (int j = 0; j < kNW; ++j)
+#pragma unroll
+                for (int m = 0; m < kRT; ++m) mma_tf32(acc[m][j], ah[m], __float_as_uint(h0[j]), __float_as_uint(h1[j]));
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < kNW; ++j) {
+        const int nt = warp + 8 * j, l = l0 + nt * 8 + 2 * t4;          // L % 4 == 0: a pair is in range or not as a whole
+        if (nt >= ntiles || l >= L) continue;
+#pragma unroll
+        for (int m = 0; m < kRT; ++m)
+#pragma unroll
+            for (int hr = 0; hr < 2; ++hr) {
+                const int r = m * 16 + q + 8 * hr;
+                if (r < R) *reinterpret_cast<float2*>(dz + ((int64_t)bk * R + r) * L + l) = make_float2(acc[m][j][2 * hr], acc[m][j][2 * hr + 1]);
+            }
+    }
+}
+
+// dW[k, d, r] += sum_{b in slice} sum_l g[b, k, d, l] z[b, k, r, l]: M = d (warp w = rows 16 w ..), N = r (kRN n-tiles of 8), K = l.
+// CTA = (128 d rows, k, a slice of the batch); partial sums go to dW with red.global.add (dW is zeroed by the caller).
+template <int kRN>
+__global__ void __launch_bounds__(kBwThreads)
+dtproj_dw_kernel(const float* __restrict__ g, const float* __restrict__ z, float* __restrict__ dW, int B, int D, int R, int L, int K,
+                 int64_t z_sb, int64_t z_sk, int nb) {
+    extern __shared__ __align__(16) float smem[];
+    float (*sG)[kDwMT * kDwPitch] = reinterpret_cast<float (*)[kDwMT * kDwPitch]>(smem);
+    float (*sZ)[kRN * 8 * kDwPitch] = reinterpret_cast<float (*)[kRN * 8 * kDwPitch]>(smem + 2 * kDwMT * kDwPitch);   // tf32 heads
+    float (*sZl)[kRN * 8 * kDwPitch] = sZ + 2;                                                                      // tf32 tails
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = lane >> 2, t4 = lane & 3;
+    const int d0 = blockIdx.x * kDwMT, k = blockIdx.y, b_lo = blockIdx.z * nb, b_hi = min(B, b_lo + nb);
+    const int lchunks = (L + kDwLC - 1) / kDwLC, items = (b_hi - b_lo) * lchunks;
+    auto issue = [&](int it) {
+        const int bi = it / lchunks, lc = it - bi * lchunks, b = b_lo + bi, lbase = lc * kDwLC;
+        const float* __restrict__ gb = g + ((int64_t)b * K + k) * D * L;
+        const float* __restrict__ zb = z + (int64_t)b * z_sb + (int64_t)k * z_sk;
+        float* dg = sG[it & 1];
+        float* dzt = sZ[it & 1];
+#pragma unroll
+        for (int i = 0; i < (kDwMT * 8) / kBwThreads; ++i) {          // 128 rows x 8 pieces
+            const int e = tid + i * kBwThreads, r = e >> 3, c4 = e & 7, d = d0 + r, l = lbase + 4 * c4;
+            const bool in = d < D && l < L;
+            cp_async16_zfill(dg + r * kDwPitch + 4 * c4, in ? gb + (int64_t)d * L + l : gb, in);
+        }
+        for (int e = tid; e < kRN * 8 * 8; e += kBwThreads) {
+            const int r = e >> 3, c4 = e & 7, l = lbase + 4 * c4;
+            const bool in = r < R && l < L;
+            cp_async16_zfill(dzt + r * kDwPitch + 4 * c4, in ? zb + (int64_t)r * L + l : zb, in);
+        }
+        cp_async_commit();
+    };
+    float acc[kRN][4];
+#pragma unroll
+    for (int n = 0; n < kRN; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[n][e] = 0.0f;
+    if (items > 0) issue(0);
+    for (int it = 0; it < items; ++it) {
+        if (it + 1 < items) { issue(it + 1); cp_async_wait<1>(); } else cp_async_wait<0>();
+        for (int e = tid; e < kRN * 8 * 8; e += kBwThreads) {       // the z pieces this thread copied: head / tail split, shared by all warps
+            float* pz = sZ[it & 1] + (e >> 3) * kDwPitch + 4 * (e & 7);
+            const float4 v = *reinterpret_cast<const float4*>(pz);
+            float4 h, t;
+            tf32_split(v.x, h.x, t.x); tf32_split(v.y, h.y, t.y); tf32_split(v.z, h.z, t.z); tf32_split(v.w, h.w, t.w);
+            *reinterpret_cast<float4*>(pz) = h;
+            *reinterpret_cast<float4*>(sZl[it & 1] + (e >> 3) * kDwPitch + 4 * (e & 7)) = t;
+        }
+        __syncthreads();
+        const float* __restrict__ ga = sG[it & 1] + (warp * 16 + q) * kDwPitch + t4;
+        const float* __restrict__ zt = sZ[it & 1] + q * kDwPitch + t4;
+        const float* __restrict__ zl = sZl[it & 1] + q * kDwPitch + t4;
+#pragma unroll
+        for (int ks = 0; ks < kDwLC / 8; ++ks) {
+            float4 hi, lo;                    // a0 (d = q, l = t4), a1 (q + 8, t4), a2 (q, t4 + 4), a3 (q + 8, t4 + 4)
+            tf32_split(ga[ks * 8], hi.x, lo.x); tf32_split(ga[8 * kDwPitch + ks * 8], hi.y, lo.y);
+            tf32_split(ga[ks * 8 + 4], hi.z, lo.z); tf32_split(ga[8 * kDwPitch + ks * 8 + 4], hi.w, lo.w);
+            const uint4 ah = make_uint4(__float_as_uint(hi.x), __float_as_uint(hi.y), __float_as_uint(hi.z), __float_as_uint(hi.w));
+            const uint4 al = make_uint4(__float_as_uint(lo.x), __float_as_uint(lo.y), __float_as_uint(lo.z), __float_as_uint(lo.w));
+            float h0[kRN], h1[kRN], t0[kRN], t1[kRN];
+#pragma unroll
+            for (int n = 0; n < kRN; ++n) {   // b0 (l = t4, r = q), b1 (l = t4 + 4, r = q)
+                h0[n] = zt[n * 8 * kDwPitch + ks * 8]; t0[n] = zl[n * 8 * kDwPitch + ks * 8];
+                h1[n] = zt[n * 8 * kDwPitch + ks * 8 + 4]; t1[n] = zl[n * 8 * kDwPitch + ks * 8 + 4];
+            }
+#pragma unroll
+            for (int n = 0; n < kRN; ++n) mma_tf32(acc[n], al, __float_as_uint(h0[n]), __float_as_uint(h1[n]));
+#pragma unroll
+            for (int n = 0; n < kRN; ++n) mma_tf32(acc[n], ah, __float_as_uint(t0[n]), __float_as_uint(t1[n]));
+#pragma unroll
+            for (int n = 0; n < kRN; ++n) mma_tf32(acc[n], ah, __float_as_uint(h0[n]), __float_as_uint(h1[n]));
+        }
+        __syncthreads();
+    }
+    // c0, c1: (d = q, r = 2 t4, 2 t4 + 1); c2, c3: d = q + 8
+#pragma unroll
+    for (int n = 0; n < kRN; ++n)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int d = d0 + warp * 16 + q + 8 * (e >> 1), r = n * 8 + 2 * t4 + (e & 1);
+            if (d < D && r < R) atomicAdd(dW + ((int64_t)k * D + d) * R + r, acc[n][e]);
+        }
+}
+
+// g: (B, K*D, L) f32 contiguous; z as in the forward; dz: (B, K, R, L) f32 contiguous or NULL; dW: (K, D, R) f32, ZEROED by the caller, or NULL
+int launch_dtproj_bwd(const float* g, const float* z, const float* W, float* dz, float* dW, int64_t B, int64_t K, int64_t D, int64_t R,
+                      int64_t L, int64_t z_sb, int64_t z_sk, cudaStream_t st) {
+    if (R > kDtMaxRank) return XFS_ERR_UNSUPPORTED;
+    if (L % 4 != 0 || z_sb % 4 != 0 || z_sk % 4 != 0) return XFS_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(dz)) % 16 != 0) return XFS_ERR_ALIGN;
+    if (B * K > 65535 * 32) return XFS_ERR_SHAPE;
+    if (dz) {
+        const int64_t L8 = (L + 7) / 8 * 8;
+        const int64_t ltiles = (L8 + 255) / 256;                                  // narrower tiles to fill the GPU at small B*K measured slower (the W^T chunk is re-staged per CTA)
+        const int NT = (int)(((L + ltiles - 1) / ltiles + 7) / 8 * 8);        // <= 256 columns per CTA, balanced over the tiles
+        const int pitch = NT + ((8 - NT % 32) + 32) % 32;
+        const int nw = (NT / 8 + 7) / 8, rt = (int)((R + 15) / 16);
+        const dim3 grid((unsigned)((L + NT - 1) / NT), (unsigned)(B * K));
+        const size_t smem = sizeof(float) * ((size_t)rt * (kDzKC / 8) * 2 * 32 * 4 + (size_t)2 * kDzKC * pitch);
+#define XFS_DZ(RT, NW)                                                                                                  \
+    do {                                                                                                                \
+        cudaFuncSetAttribute(dtproj_dz_kernel<RT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+        dtproj_dz_kernel<RT, NW><<<grid, kBwThreads, smem, st>>>(g, W, dz, (int)D, (int)R, (int)L, (int)K, NT, pitch);   \
+    } while (0)
+#define XFS_DZ_R(NW) do { if (rt == 1) XFS_DZ(1, NW); else if (rt == 2) XFS_DZ(2, NW); else if (rt == 3) XFS_DZ(3, NW); else XFS_DZ(4, NW); } while (0)
+        if (nw == 1) XFS_DZ_R(1); else if (nw == 2) XFS_DZ_R(2); else if (nw == 3) XFS_DZ_R(3); else XFS_DZ_R(4);
+#undef XFS_DZ_R
+#undef XFS_DZ
+        const int rc = check_launch();
+        if (rc) return rc;
+    }
+    if (dW) {
+        const int64_t blocks = ((D + kDwMT - 1) / kDwMT) * K;
+        int64_t slices = (148 * 4 + blocks - 1) / blocks;               // ~4 CTAs per SM in flight
+        if (slices > B) slices = B;
+        const int nb = (int)((B + slices - 1) / slices);
+        const dim3 grid((unsigned)((D + kDwMT - 1) / kDwMT), (unsigned)K, (unsigned)((B + nb - 1) / nb));
+        const int rn = (int)((R + 7) / 8);
+        const size_t smem = sizeof(float) * 2 * ((size_t)kDwMT + 2 * 8 * rn) * kDwPitch;
+#define XFS_DW(N)                                                                                                       \
+    do {                                                                                                                \
+        cudaFuncSetAttribute(dtproj_dw_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
+        dtproj_dw_kernel<N><<<grid, kBwThreads, smem, st>>>(g, z, dW, (int)B, (int)D, (int)R, (int)L, (int)K, z_sb, z_sk, nb); \
+    } while (0)
+        switch (rn) {
+            case 1: XFS_DW(1); break; case 2: XFS_DW(2); break; case 3: XFS_DW(3); break; case 4: XFS_DW(4); break;
+            case 5: XFS_DW(5); break; case 6: XFS_DW(6); break; case 7: XFS_DW(7); break; default: XFS_DW(8); break;
+        }
+#undef XFS_DW
+        return check_launch();
+    }
+    return XFS_OK;
+}
+
 }  // namespace xfs

@@ -43,10 +43,26 @@ class DtProjFn(torch.autograd.Function):
         z, w = ctx.saved_tensors
         B, K, R, L = z.shape
         D = w.shape[1]
-        # two plain batched GEMMs (library work): dz = W^T g over D, dW = sum_b g z^T over L then the batch
-        g4 = g.contiguous().to(z.dtype).view(B, K, D, L)
-        dz = torch.matmul(w.transpose(1, 2).unsqueeze(0).to(g4.dtype), g4) if ctx.needs_input_grad[0] else None
-        dw = torch.matmul(g4, z.transpose(2, 3)).float().sum(0).to(ctx.wdtype) if ctx.needs_input_grad[1] else None
+        need_z, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        g = g.contiguous()
+        L_ = _lib.lib()
+        if (g.dtype == torch.float32 and z.dtype == torch.float32 and g.data_ptr() % 16 == 0 and z.data_ptr() % 16 == 0
+                and L_.xfs_dt_proj_bwd_supported(R, L, z.stride(0), z.stride(1), _lib.dtype_code(z))):
+            # hand-written: one pass over g for each of dz = W^T g and dW = sum_{b,l} g z^T (3xTF32 warp MMA, csrc/dtproj.cu)
+            dev = g.device
+            dz = torch.empty((B, K, R, L), dtype=torch.float32, device=dev) if need_z else None
+            dw = torch.zeros((K, D, R), dtype=torch.float32, device=dev) if need_w else None
+            if need_z or need_w:
+                with torch.cuda.device(dev):
+                    rc = L_.xfs_dt_proj_bwd(_lib.ptr(g), _lib.ptr(z), _lib.ptr(w), _lib.ptr(dz) if need_z else None,
+                                            _lib.ptr(dw) if need_w else None, B, K, D, R, L, z.stride(0), z.stride(1),
+                                            _lib.dtype_code(z), _lib.stream(dev))
+                _lib.check(rc, "dt_proj_bwd")
+            return dz, (dw.to(ctx.wdtype) if need_w else None)
+        # 16-bit rows, L % 4 != 0: two plain batched GEMMs (library work): dz = W^T g over D, dW = sum_b g z^T over L then the batch
+        g4 = g.to(z.dtype).view(B, K, D, L)
+        dz = torch.matmul(w.transpose(1, 2).unsqueeze(0).to(g4.dtype), g4) if need_z else None
+        dw = torch.matmul(g4, z.transpose(2, 3)).float().sum(0).to(ctx.wdtype) if need_w else None
         return dz, dw
 
 
