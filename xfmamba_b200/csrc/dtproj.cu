@@ -147,14 +147,13 @@ struct DtMma {
     bool vec4, vec2;                 // 16-byte z loads / 4-position delta stores allowed
 };
 
-__device__ __forceinline__ uint32_t tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
+// x = hi + lo with hi, lo valid tf32 bit patterns (low 13 mantissa bits zero).  By masking, not `cvt.rna.tf32.f32`: the conversion
+// issues on the XU pipe (a quarter-rate unit shared with the transcendentals), and at two conversions per operand element it, not the
+// tensor pipe, bounded these kernels (ncu: xu pipe saturated, 25 % of all instructions).  Truncation leaves |lo| < 2^-10 |x| and drops
+// 2^-20 |x| from lo: ~1e-6 relative per product, two orders under the parity bar.
 __device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
-    hi = __uint_as_float(tf32_rna(x));
-    lo = __uint_as_float(tf32_rna(x - hi));
+    hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    lo = __uint_as_float(__float_as_uint(x - hi) & 0xffffe000u);
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint4& a, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
