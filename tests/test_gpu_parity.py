@@ -782,6 +782,24 @@ def test_dt_proj_fwd_bwd_vs_oracle(B, K, R, D, L, sliced):
     assert rel_err(n(wt.grad), dw) < TOL32
 
 
+@pytest.mark.parametrize("which", ["z", "w"])
+def test_dt_proj_bwd_single_gradient(which):
+    """only dz or only dW requested: the other output pointer of xfs_dt_proj_bwd is NULL"""
+    from xfmamba_b200.proj import dt_proj
+    rng = np.random.default_rng(11)
+    B, K, R, D, L = 3, 4, 12, 100, 196
+    z = rng.standard_normal((B, K, R, L)).astype(np.float32)
+    w = (rng.standard_normal((K, D, R)) * R ** -0.5).astype(np.float32)
+    g = rng.standard_normal((B, K * D, L)).astype(np.float32)
+    zt, wt = t(z).requires_grad_(which == "z"), t(w).requires_grad_(which == "w")
+    dt_proj(zt, wt).backward(t(g))
+    dz, dw = oracle.dt_proj_bwd(z, w, g)
+    if which == "z":
+        assert wt.grad is None and rel_err(n(zt.grad), dz) < TOL32
+    else:
+        assert zt.grad is None and rel_err(n(wt.grad), dw) < TOL32
+
+
 def test_dt_proj_bf16():
     from xfmamba_b200.proj import dt_proj
     torch.manual_seed(2)
