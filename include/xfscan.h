@@ -342,8 +342,8 @@ XFS_API int xfs_dt_proj_fwd(const void* z, const float* W, void* delta, int64_t 
 /* Backward of the projection, one pass over g each: dz[b,k,r,l] = sum_d W[k,d,r] g[b,k*D+d,l] and
  * dW[k,d,r] += sum_{b,l} g[b,k*D+d,l] z[b,k,r,l] (the autograd of the grouped conv1d above; the reference leaves it to cuDNN).
  * g: (B, K*D, L) contiguous; z as in the forward; dz: (B, K, R, L) f32 contiguous, may be NULL; dW: (K, D, R) f32, accumulated
- * into (zero it first), may be NULL.  f32 rows with L % 4 == 0 and 16-byte aligned bases / strides only
- * (xfs_dt_proj_bwd_supported); otherwise XFS_ERR_UNSUPPORTED and the caller uses its library GEMMs. */
+ * into (zero it first), may be NULL.  f32 rows only (xfs_dt_proj_bwd_supported; 16-bit rows: XFS_ERR_UNSUPPORTED and the caller uses
+ * its library GEMMs); rows that are not 16-byte aligned (L % 4 != 0, odd strides) are copied in 4-byte pieces. */
 XFS_API int xfs_dt_proj_bwd_supported(int64_t R, int64_t L, int64_t z_batch_stride, int64_t z_route_stride, int dtype);
 XFS_API int xfs_dt_proj_bwd(const void* g, const void* z, const float* W, void* dz, float* dW, int64_t B, int64_t K, int64_t D, int64_t R,
                             int64_t L, int64_t z_batch_stride, int64_t z_route_stride, int dtype, xfs_stream_t stream);

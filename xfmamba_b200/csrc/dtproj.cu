@@ -446,10 +446,10 @@ int launch_dtproj_fwd(const void* z, const float* W, void* out, int64_t B, int64
     return check_launch();
 }
 
-// ---- backward on the tensor pipe (fp32 rows, L % 4 == 0): dz = W^T g and dW = sum_{b,l} g z^T, one pass over g each -----------------
+// ---- backward on the tensor pipe (fp32 rows): dz = W^T g and dW = sum_{b,l} g z^T, one pass over g each -----------------
 // cuBLAS ran these as two batched SIMT sgemms (matmul does not use TF32) plus a reduction over the batch: 274 us per 14x14 block
 // of XFMamba-B (B = 64, R = 32, D = 1024) against 31 us for reading g once.  Same 3xTF32 arithmetic as the forward; the g tiles are
-// streamed with cp.async (16-byte pieces, zero fill out of range) through a two-slot ring, the small operand is split at staging or at use.
+// streamed with cp.async (16-byte pieces, 4-byte ones when L % 4 != 0 or a base is unaligned; zero fill out of range) through a two-slot ring, the small operand is split at staging or at use.
 constexpr int kBwThreads = 256;
 constexpr int kDzKC = 32;            // dz: d rows of g per ring slot (4 k-steps)
 constexpr int kDwLC = 32;            // dW: columns of g / z per ring slot (4 k-steps)
@@ -460,16 +460,32 @@ __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsr
     const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gsrc), "r"(in ? 16 : 0));
 }
+// four consecutive floats [l, l + 4) of a global row of L floats -> 16-byte aligned shared memory, zeros where l >= L or !row_ok.
+// vec: rows are 16-byte aligned and L % 4 == 0 (one 16-byte copy); otherwise four 4-byte copies with their own bounds.
+__device__ __forceinline__ void cp_async_row4(float* smem_dst, const float* row, int l, int L, bool row_ok, bool vec) {
+    if (vec) {
+        const bool in = row_ok && l < L;
+        cp_async16_zfill(smem_dst, in ? row + l : row, in);
+    } else {
+        const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smem_dst);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool in = row_ok && l + i < L;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(sa + 4 * i), "l"(in ? row + l + i : row), "r"(in ? 4 : 0));
+        }
+    }
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
 template <int kN>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kN) : "memory"); }
 
 // dz[b, k, r, l] = sum_d W[k, d, r] g[b, k, d, l]: M = r (kRT m-tiles of 16), N = l, K = d.  CTA = (b, k, NT <= 256 columns); warp w owns
 // n-tiles w, w + 8, ... (kNW of them), so one W^T chunk (staged once per CTA and 32 d rows, head / tail split there) serves up to 32 n-tiles.
-template <int kRT, int kNW>
+template <int kRT, int kNW, bool kVec>
 __global__ void __launch_bounds__(kBwThreads)
 dtproj_dz_kernel(const float* __restrict__ g, const float* __restrict__ W, float* __restrict__ dz, int D, int R, int L, int K, int NT,
                  int pitch) {
+    constexpr bool vec = kVec;
     extern __shared__ __align__(16) float smem[];
     float* sA = smem;                                          // [m-tile][k-step][hi, lo][lane] float4, fragment order
     float* sG = smem + kRT * (kDzKC / 8) * 2 * 32 * 4;         // [2 slots][32 d rows][pitch], pitch = 8 (mod 32)
@@ -482,11 +498,8 @@ dtproj_dz_kernel(const float* __restrict__ g, const float* __restrict__ W, float
         float* dst = sG + (c & 1) * kDzKC * pitch;
         for (int r = warp; r < kDzKC; r += kBwThreads / 32) {
             const int d = c * kDzKC + r;
-            for (int c4 = lane; c4 < p4; c4 += 32) {
-                const int l = l0 + 4 * c4;
-                const bool in = d < D && l < L;
-                cp_async16_zfill(dst + r * pitch + 4 * c4, in ? gb + (int64_t)d * L + l : gb, in);
-            }
+            for (int c4 = lane; c4 < p4; c4 += 32)
+                cp_async_row4(dst + r * pitch + 4 * c4, gb + (int64_t)(d < D ? d : 0) * L, l0 + 4 * c4, L, d < D, vec);
         }
         cp_async_commit();
     };
@@ -550,24 +563,31 @@ dtproj_dz_kernel(const float* __restrict__ g, const float* __restrict__ W, float
     }
 #pragma unroll
     for (int j = 0; j < kNW; ++j) {
-        const int nt = warp + 8 * j, l = l0 + nt * 8 + 2 * t4;          // L % 4 == 0: a pair is in range or not as a whole
+        const int nt = warp + 8 * j, l = l0 + nt * 8 + 2 * t4;          // vec: a pair is in range or not as a whole, and 8-byte aligned
         if (nt >= ntiles || l >= L) continue;
 #pragma unroll
         for (int m = 0; m < kRT; ++m)
 #pragma unroll
             for (int hr = 0; hr < 2; ++hr) {
                 const int r = m * 16 + q + 8 * hr;
-                if (r < R) *reinterpret_cast<float2*>(dz + ((int64_t)bk * R + r) * L + l) = make_float2(acc[m][j][2 * hr], acc[m][j][2 * hr + 1]);
+                if (r >= R) continue;
+                float* __restrict__ o = dz + ((int64_t)bk * R + r) * L + l;
+                if (vec) *reinterpret_cast<float2*>(o) = make_float2(acc[m][j][2 * hr], acc[m][j][2 * hr + 1]);
+                else {
+                    o[0] = acc[m][j][2 * hr];
+                    if (l + 1 < L) o[1] = acc[m][j][2 * hr + 1];
+                }
             }
     }
 }
 
 // dW[k, d, r] += sum_{b in slice} sum_l g[b, k, d, l] z[b, k, r, l]: M = d (warp w = rows 16 w ..), N = r (kRN n-tiles of 8), K = l.
 // CTA = (128 d rows, k, a slice of the batch); partial sums go to dW with red.global.add (dW is zeroed by the caller).
-template <int kRN>
+template <int kRN, bool kVec>
 __global__ void __launch_bounds__(kBwThreads)
 dtproj_dw_kernel(const float* __restrict__ g, const float* __restrict__ z, float* __restrict__ dW, int B, int D, int R, int L, int K,
                  int64_t z_sb, int64_t z_sk, int nb) {
+    constexpr bool vec = kVec;
     extern __shared__ __align__(16) float smem[];
     float (*sG)[kDwMT * kDwPitch] = reinterpret_cast<float (*)[kDwMT * kDwPitch]>(smem);
     float (*sZ)[kRN * 8 * kDwPitch] = reinterpret_cast<float (*)[kRN * 8 * kDwPitch]>(smem + 2 * kDwMT * kDwPitch);   // tf32 heads
@@ -583,14 +603,12 @@ dtproj_dw_kernel(const float* __restrict__ g, const float* __restrict__ z, float
         float* dzt = sZ[it & 1];
 #pragma unroll
         for (int i = 0; i < (kDwMT * 8) / kBwThreads; ++i) {          // 128 rows x 8 pieces
-            const int e = tid + i * kBwThreads, r = e >> 3, c4 = e & 7, d = d0 + r, l = lbase + 4 * c4;
-            const bool in = d < D && l < L;
-            cp_async16_zfill(dg + r * kDwPitch + 4 * c4, in ? gb + (int64_t)d * L + l : gb, in);
+            const int e = tid + i * kBwThreads, r = e >> 3, c4 = e & 7, d = d0 + r;
+            cp_async_row4(dg + r * kDwPitch + 4 * c4, gb + (int64_t)(d < D ? d : 0) * L, lbase + 4 * c4, L, d < D, vec);
         }
         for (int e = tid; e < kRN * 8 * 8; e += kBwThreads) {
-            const int r = e >> 3, c4 = e & 7, l = lbase + 4 * c4;
-            const bool in = r < R && l < L;
-            cp_async16_zfill(dzt + r * kDwPitch + 4 * c4, in ? zb + (int64_t)r * L + l : zb, in);
+            const int r = e >> 3, c4 = e & 7;
+            cp_async_row4(dzt + r * kDwPitch + 4 * c4, zb + (int64_t)(r < R ? r : 0) * L, lbase + 4 * c4, L, r < R, vec);
         }
         cp_async_commit();
     };
@@ -650,8 +668,8 @@ dtproj_dw_kernel(const float* __restrict__ g, const float* __restrict__ z, float
 int launch_dtproj_bwd(const float* g, const float* z, const float* W, float* dz, float* dW, int64_t B, int64_t K, int64_t D, int64_t R,
                       int64_t L, int64_t z_sb, int64_t z_sk, cudaStream_t st) {
     if (R > kDtMaxRank) return XFS_ERR_UNSUPPORTED;
-    if (L % 4 != 0 || z_sb % 4 != 0 || z_sk % 4 != 0) return XFS_ERR_UNSUPPORTED;
-    if ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(dz)) % 16 != 0) return XFS_ERR_ALIGN;
+    const bool vec = L % 4 == 0 && z_sb % 4 == 0 && z_sk % 4 == 0 &&
+                     (reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(dz)) % 16 == 0;
     if (B * K > 65535 * 32) return XFS_ERR_SHAPE;
     if (dz) {
         const int64_t L8 = (L + 7) / 8 * 8;
@@ -661,15 +679,17 @@ int launch_dtproj_bwd(const float* g, const float* z, const float* W, float* dz,
         const int nw = (NT / 8 + 7) / 8, rt = (int)((R + 15) / 16);
         const dim3 grid((unsigned)((L + NT - 1) / NT), (unsigned)(B * K));
         const size_t smem = sizeof(float) * ((size_t)rt * (kDzKC / 8) * 2 * 32 * 4 + (size_t)2 * kDzKC * pitch);
-#define XFS_DZ(RT, NW)                                                                                                  \
+#define XFS_DZ_V(RT, NW, V)                                                                                            \
     do {                                                                                                                \
-        cudaFuncSetAttribute(dtproj_dz_kernel<RT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
-        dtproj_dz_kernel<RT, NW><<<grid, kBwThreads, smem, st>>>(g, W, dz, (int)D, (int)R, (int)L, (int)K, NT, pitch);   \
+        cudaFuncSetAttribute(dtproj_dz_kernel<RT, NW, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+        dtproj_dz_kernel<RT, NW, V><<<grid, kBwThreads, smem, st>>>(g, W, dz, (int)D, (int)R, (int)L, (int)K, NT, pitch); \
     } while (0)
+#define XFS_DZ(RT, NW) do { if (vec) XFS_DZ_V(RT, NW, true); else XFS_DZ_V(RT, NW, false); } while (0)
 #define XFS_DZ_R(NW) do { if (rt == 1) XFS_DZ(1, NW); else if (rt == 2) XFS_DZ(2, NW); else if (rt == 3) XFS_DZ(3, NW); else XFS_DZ(4, NW); } while (0)
         if (nw == 1) XFS_DZ_R(1); else if (nw == 2) XFS_DZ_R(2); else if (nw == 3) XFS_DZ_R(3); else XFS_DZ_R(4);
 #undef XFS_DZ_R
 #undef XFS_DZ
+#undef XFS_DZ_V
         const int rc = check_launch();
         if (rc) return rc;
     }
@@ -681,16 +701,18 @@ int launch_dtproj_bwd(const float* g, const float* z, const float* W, float* dz,
         const dim3 grid((unsigned)((D + kDwMT - 1) / kDwMT), (unsigned)K, (unsigned)((B + nb - 1) / nb));
         const int rn = (int)((R + 7) / 8);
         const size_t smem = sizeof(float) * 2 * ((size_t)kDwMT + 2 * 8 * rn) * kDwPitch;
-#define XFS_DW(N)                                                                                                       \
+#define XFS_DW_V(N, V)                                                                                                  \
     do {                                                                                                                \
-        cudaFuncSetAttribute(dtproj_dw_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
-        dtproj_dw_kernel<N><<<grid, kBwThreads, smem, st>>>(g, z, dW, (int)B, (int)D, (int)R, (int)L, (int)K, z_sb, z_sk, nb); \
+        cudaFuncSetAttribute(dtproj_dw_kernel<N, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+        dtproj_dw_kernel<N, V><<<grid, kBwThreads, smem, st>>>(g, z, dW, (int)B, (int)D, (int)R, (int)L, (int)K, z_sb, z_sk, nb); \
     } while (0)
+#define XFS_DW(N) do { if (vec) XFS_DW_V(N, true); else XFS_DW_V(N, false); } while (0)
         switch (rn) {
             case 1: XFS_DW(1); break; case 2: XFS_DW(2); break; case 3: XFS_DW(3); break; case 4: XFS_DW(4); break;
             case 5: XFS_DW(5); break; case 6: XFS_DW(6); break; case 7: XFS_DW(7); break; default: XFS_DW(8); break;
         }
 #undef XFS_DW
+#undef XFS_DW_V
         return check_launch();
     }
     return XFS_OK;

@@ -46,7 +46,7 @@ class DtProjFn(torch.autograd.Function):
         need_z, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         g = g.contiguous()
         L_ = _lib.lib()
-        if (g.dtype == torch.float32 and z.dtype == torch.float32 and g.data_ptr() % 16 == 0 and z.data_ptr() % 16 == 0
+        if (g.dtype == torch.float32 and z.dtype == torch.float32
                 and L_.xfs_dt_proj_bwd_supported(R, L, z.stride(0), z.stride(1), _lib.dtype_code(z))):
             # hand-written: one pass over g for each of dz = W^T g and dW = sum_{b,l} g z^T (3xTF32 warp MMA, csrc/dtproj.cu)
             dev = g.device
@@ -59,7 +59,7 @@ class DtProjFn(torch.autograd.Function):
                                             _lib.dtype_code(z), _lib.stream(dev))
                 _lib.check(rc, "dt_proj_bwd")
             return dz, (dw.to(ctx.wdtype) if need_w else None)
-        # 16-bit rows, L % 4 != 0: two plain batched GEMMs (library work): dz = W^T g over D, dW = sum_b g z^T over L then the batch
+        # 16-bit rows: two plain batched GEMMs (library work): dz = W^T g over D, dW = sum_b g z^T over L then the batch
         g4 = g.to(z.dtype).view(B, K, D, L)
         dz = torch.matmul(w.transpose(1, 2).unsqueeze(0).to(g4.dtype), g4) if need_z else None
         dw = torch.matmul(g4, z.transpose(2, 3)).float().sum(0).to(ctx.wdtype) if need_w else None
