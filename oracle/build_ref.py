@@ -9,6 +9,7 @@ selective-scan kernel the reference calls at models/csms6s.py:83,101 when its ex
 """
 from __future__ import annotations
 
+import shutil
 import subprocess
 import sys
 import sysconfig
@@ -60,6 +61,7 @@ def build(verbose: bool = False) -> Path | None:
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode:
         raise RuntimeError("reference link failed:\n" + r.stderr[-3000:])
+    shutil.rmtree(obj, ignore_errors=True)           # only the .so travels to the GPU box
     return so
 
 
