@@ -283,17 +283,19 @@ dtproj_mma_fwd_kernel(const T* __restrict__ z, const float* __restrict__ W, T* _
             for (int j = 0; j < kMmaG; ++j) {
                 const int cj = j < nv ? 8 * j : 0;               // the tail group re-reads tile 0 (results discarded)
                 h0[j] = bh[ro + cj]; h1[j] = bh[ro + 4 * g.pitch + cj];
-                t0[j] = bt[ro + cj]; t1[j] = bt[ro + 4 * g.pitch + cj];
+                if constexpr (sizeof(T) == 4) { t0[j] = bt[ro + cj]; t1[j] = bt[ro + 4 * g.pitch + cj]; }
             }
             // three passes over independent accumulators: small terms first
 #pragma unroll
             for (int j = 0; j < kMmaG; ++j)
 #pragma unroll
                 for (int m = 0; m < kMW; ++m) mma_tf32(acc[m][j], al[m], h0[j], h1[j]);
+            if constexpr (sizeof(T) == 4) {       // bf16 / f16 rows are exact tf32 values: their tail is zero, two MMAs suffice
 #pragma unroll
-            for (int j = 0; j < kMmaG; ++j)
+                for (int j = 0; j < kMmaG; ++j)
 #pragma unroll
-                for (int m = 0; m < kMW; ++m) mma_tf32(acc[m][j], ah[m], t0[j], t1[j]);
+                    for (int m = 0; m < kMW; ++m) mma_tf32(acc[m][j], ah[m], t0[j], t1[j]);
+            }
 #pragma unroll
             for (int j = 0; j < kMmaG; ++j)
 #pragma unroll
