@@ -10,7 +10,7 @@
 // Two kernels: an fp32 FFMA2 kernel (first) and a 3xTF32 warp-MMA kernel (second, the default); plain TF32 would miss the 1e-4 parity bar.
 // CTA = one (b, k), NCG groups of 8 channels x PG groups of 4 positions; z tile [R][4*PG] and W tile [R][8*NCG] in shared
 // memory; a thread owns 8 channels x 4 positions (packed FFMA2 over position pairs), items flattened so that short rows
-// (L = 196, 49) still fill the CTA.  The backward (dz = W^T g, dW = sum_b g z^T) is two plain batched GEMMs and goes to cuBLAS from proj.py.
+// (L = 196, 49) still fill the CTA.  The backward (dz = W^T g, dW = sum_{b,l} g z^T) is the pair of MMA kernels at the end of this file.
 #include <cstdlib>
 #include "xfscan_common.cuh"
 
@@ -129,8 +129,8 @@ dtproj_fwd_kernel(const T* __restrict__ z, const float* __restrict__ W, T* __res
 // The FFMA2 kernel above is bound by shared-memory operand traffic (ncu: LSU wavefronts 86 %, FMA pipe 66 %) at 1.8-2.8 TB/s of
 // delta for the 28x28 / 14x14 stages.  The contraction is a batched (D x R) x (R x L) product with R <= 64, so the legacy warp
 // MMA (mma.sync m16n8k8, tf32 in / fp32 accumulate) does it with 1/6 of the operand loads; fp32 accuracy is kept by splitting both
-// operands into a tf32 head and a tf32 tail (x = hi + lo, 21 significant bits; z at staging time, W at use) and issuing three MMAs per tile,
-// lo*hi + hi*lo + hi*hi (the dropped lo*lo term is 2^-22 relative).  tcgen05 is not used: K = R is 8..64, the tiles are tiny and
+// operands into a tf32 head and a tf32 tail (x = hi + lo, ~20 significant bits, split by masking; z at staging time, W at use) and issuing three MMAs per tile,
+// lo*hi + hi*lo + hi*hi (the dropped lo*lo term is 2^-20 relative).  tcgen05 is not used: K = R is 8..64, the tiles are tiny and
 // the kernel only has to stay under the time it takes to write delta.
 // CTA = 8 warps, (k, NB images, 16*4*kMW channels, <= 256 positions); warp w owns kMW m-tiles (16 channels each) and sweeps the
 // n-tiles (8 positions) in groups of 4, even groups for warps 0-3 and odd groups for warps 4-7.  W is staged in fragment order (one LDS.128 per m-tile and k-step), z as [r][column] hi / lo
